@@ -1,0 +1,559 @@
+// capi.cu -- the C ABI of libvpdq_b200.so (include/vpdq_b200.h): argument checking, the streaming
+// hasher handle (pinned staging ring + copy/compute overlap), the resident hash-DB handle and the
+// host-pointer convenience calls.  All compute is in pdq_kernels.cu / hamming_kernels.cu; there is
+// no CPU implementation of anything here.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vpdq {
+
+static thread_local char t_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return e == cudaErrorMemoryAllocation ? VPDQ_B200_ERR_NOMEM : VPDQ_B200_ERR_CUDA;
+}
+
+static int check_frames(const void* frames, int channels, int64_t n, int width, int height) {
+    if (n < 0 || (channels != 3 && channels != 1)) {
+        set_error("invalid argument: n_frames=%lld channels=%d", (long long)n, channels);
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (width != kDim || height != kDim) {
+        set_error("unsupported frame size %dx%d (the kernels are specialised for 512x512, vpdqpy.py:23)", width,
+                  height);
+        return VPDQ_B200_ERR_UNSUPPORTED;
+    }
+    if (n > 0 && !frames) {
+        set_error("frames pointer is NULL");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return VPDQ_B200_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    int rc = VPDQ_B200_OK;
+    explicit DeviceGuard(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e == cudaSuccess && dev >= 0 && dev != prev) e = cudaSetDevice(dev);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
+        if (dev < 0) prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace vpdq
+
+using namespace vpdq;
+
+// ====================================================================================================
+// streaming hasher
+// ====================================================================================================
+namespace {
+constexpr int kSlots = 3;         // pinned staging ring depth
+constexpr int kSlotFrames = 32;   // frames per staged batch (25 MB RGB)
+
+struct Slot {
+    uint8_t* h_frames = nullptr;  // pinned
+    uint8_t* d_frames = nullptr;
+    uint8_t* h_hash = nullptr;    // pinned results
+    int32_t* h_quality = nullptr;
+    uint8_t* d_hash = nullptr;
+    int32_t* d_quality = nullptr;
+    cudaEvent_t done = nullptr;
+    int filled = 0;     // frames memcpy'd into h_frames, not yet submitted
+    int in_flight = 0;  // frames submitted, results not yet collected
+};
+}  // namespace
+
+struct vpdq_b200_hasher {
+    int device = 0, channels = 3;
+    size_t frame_bytes = 0;
+    cudaStream_t stream = nullptr;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    Slot slots[kSlots];
+    int cur = 0;
+    int64_t pushed = 0;
+    std::vector<uint8_t> hashes;    // collected, in push order
+    std::vector<int32_t> quality;
+    std::mutex mu;
+};
+
+static void hasher_free(vpdq_b200_hasher* h) {
+    for (Slot& s : h->slots) {
+        if (s.h_frames) cudaFreeHost(s.h_frames);
+        if (s.d_frames) cudaFree(s.d_frames);
+        if (s.h_hash) cudaFreeHost(s.h_hash);
+        if (s.h_quality) cudaFreeHost(s.h_quality);
+        if (s.d_hash) cudaFree(s.d_hash);
+        if (s.d_quality) cudaFree(s.d_quality);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// wait for a slot's batch and move its results to the host vectors
+static int slot_collect(vpdq_b200_hasher* h, Slot& s) {
+    if (s.in_flight == 0) return VPDQ_B200_OK;
+    VPDQ_CUDA(cudaEventSynchronize(s.done));
+    h->hashes.insert(h->hashes.end(), s.h_hash, s.h_hash + (size_t)s.in_flight * 32);
+    h->quality.insert(h->quality.end(), s.h_quality, s.h_quality + s.in_flight);
+    s.in_flight = 0;
+    return VPDQ_B200_OK;
+}
+
+static int slot_submit(vpdq_b200_hasher* h, Slot& s) {
+    if (s.filled == 0) return VPDQ_B200_OK;
+    const int n = s.filled;
+    VPDQ_CUDA(cudaMemcpyAsync(s.d_frames, s.h_frames, (size_t)n * h->frame_bytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = pdq_launch(s.d_frames, h->channels, n, s.d_hash, s.d_quality, nullptr, nullptr, h->d_scratch,
+                        h->scratch_bytes, h->stream);
+    if (rc) return rc;
+    VPDQ_CUDA(cudaMemcpyAsync(s.h_hash, s.d_hash, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    VPDQ_CUDA(cudaMemcpyAsync(s.h_quality, s.d_quality, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    VPDQ_CUDA(cudaEventRecord(s.done, h->stream));
+    s.in_flight = n;
+    s.filled = 0;
+    return VPDQ_B200_OK;
+}
+
+extern "C" {
+
+const char* vpdq_b200_last_error(void) { return t_err; }
+int vpdq_b200_abi_version(void) { return 1; }
+
+int vpdq_b200_device_count(int* count) {
+    if (!count) return VPDQ_B200_ERR_INVALID;
+    *count = 0;
+    VPDQ_CUDA(cudaGetDeviceCount(count));
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_dct_matrix(float* out) {
+    if (!out) return VPDQ_B200_ERR_INVALID;
+    memcpy(out, pdq_host_dct(), sizeof(float) * 16 * 64);
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_pdq_scratch_bytes(int64_t n_frames, size_t* bytes) {
+    if (!bytes || n_frames < 0) return VPDQ_B200_ERR_INVALID;
+    *bytes = pdq_scratch_bytes(n_frames);
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_pdq_stages_dev(const uint8_t* d_frames, int channels, int64_t n_frames, int width, int height,
+                             uint8_t* d_hashes, int32_t* d_quality, float* d_a64, float* d_b16, void* d_scratch,
+                             size_t scratch_bytes, void* stream) {
+    int rc = check_frames(d_frames, channels, n_frames, width, height);
+    if (rc) return rc;
+    if (n_frames == 0) return VPDQ_B200_OK;
+    if (!d_hashes || !d_quality || !d_scratch) {
+        set_error("output / scratch pointer is NULL");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (((uintptr_t)d_frames & 15) || ((uintptr_t)d_hashes & 3) || ((uintptr_t)d_scratch & 15)) {
+        set_error("alignment: frames and scratch need 16 bytes, hashes 4 bytes");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return pdq_launch(d_frames, channels, n_frames, d_hashes, d_quality, d_a64, d_b16, d_scratch, scratch_bytes,
+                      (cudaStream_t)stream);
+}
+
+int vpdq_b200_pdq_hash_frames_dev(const uint8_t* d_frames, int channels, int64_t n_frames, int width, int height,
+                                  uint8_t* d_hashes, int32_t* d_quality, void* d_scratch, size_t scratch_bytes,
+                                  void* stream) {
+    return vpdq_b200_pdq_stages_dev(d_frames, channels, n_frames, width, height, d_hashes, d_quality, nullptr,
+                                    nullptr, d_scratch, scratch_bytes, stream);
+}
+
+int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_t n_frames, int width, int height,
+                                   uint8_t* h_hashes, int32_t* h_quality, int device) {
+    int rc = check_frames(h_frames, channels, n_frames, width, height);
+    if (rc) return rc;
+    if (n_frames == 0) return VPDQ_B200_OK;
+    if (!h_hashes || !h_quality) {
+        set_error("output pointer is NULL");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+
+    // two chunks in flight: the H2D copy of chunk c+1 overlaps the kernels of chunk c
+    const int64_t chunk = n_frames < 256 ? n_frames : 256;
+    const size_t fb = (size_t)kPlane * channels;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    uint8_t* d_in[2] = {nullptr, nullptr};
+    void* d_scr[2] = {nullptr, nullptr};
+    uint8_t* d_hash = nullptr;
+    int32_t* d_q = nullptr;
+    const size_t scr = pdq_scratch_bytes(chunk);
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) {
+            if (st[b]) cudaStreamSynchronize(st[b]);
+            if (d_in[b]) cudaFree(d_in[b]);
+            if (d_scr[b]) cudaFree(d_scr[b]);
+            if (st[b]) cudaStreamDestroy(st[b]);
+        }
+        if (d_hash) cudaFree(d_hash);
+        if (d_q) cudaFree(d_q);
+    };
+#define HOST_TRY(call)                                \
+    do {                                              \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess) {                     \
+            cleanup();                                \
+            return ::vpdq::cuda_fail(e__, #call);     \
+        }                                             \
+    } while (0)
+    const int nbuf = n_frames > chunk ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) {
+        HOST_TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
+        HOST_TRY(cudaMalloc(&d_in[b], (size_t)chunk * fb));
+        HOST_TRY(cudaMalloc(&d_scr[b], scr));
+    }
+    HOST_TRY(cudaMalloc(&d_hash, (size_t)n_frames * 32));
+    HOST_TRY(cudaMalloc(&d_q, (size_t)n_frames * sizeof(int32_t)));
+    int c = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, ++c) {
+        const int b = c % nbuf;
+        const int64_t nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        HOST_TRY(cudaMemcpyAsync(d_in[b], h_frames + (size_t)f0 * fb, (size_t)nf * fb, cudaMemcpyHostToDevice, st[b]));
+        rc = pdq_launch(d_in[b], channels, nf, d_hash + (size_t)f0 * 32, d_q + f0, nullptr, nullptr, d_scr[b], scr,
+                        st[b]);
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+        HOST_TRY(cudaMemcpyAsync(h_hashes + (size_t)f0 * 32, d_hash + (size_t)f0 * 32, (size_t)nf * 32,
+                                 cudaMemcpyDeviceToHost, st[b]));
+        HOST_TRY(cudaMemcpyAsync(h_quality + f0, d_q + f0, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st[b]));
+    }
+    for (int b = 0; b < nbuf; ++b) HOST_TRY(cudaStreamSynchronize(st[b]));
+#undef HOST_TRY
+    cleanup();
+    return VPDQ_B200_OK;
+}
+
+// ---- hasher handle -----------------------------------------------------------------------------------
+int vpdq_b200_hasher_create(int device, int width, int height, int channels, int num_threads,
+                            vpdq_b200_hasher** out) {
+    (void)num_threads;  // the reference's CPU pool size (vpdqpy.py:113); the GPU is the pool here
+    if (!out) return VPDQ_B200_ERR_INVALID;
+    *out = nullptr;
+    int rc = check_frames((const void*)1, channels, 0, width, height);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+    vpdq_b200_hasher* h = new (std::nothrow) vpdq_b200_hasher;
+    if (!h) return VPDQ_B200_ERR_NOMEM;
+    cudaError_t e = cudaGetDevice(&h->device);
+    h->channels = channels;
+    h->frame_bytes = (size_t)kPlane * channels;
+    h->scratch_bytes = pdq_scratch_bytes(kSlotFrames);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_scratch, h->scratch_bytes);
+    for (int i = 0; i < kSlots && e == cudaSuccess; ++i) {
+        Slot& s = h->slots[i];
+        e = cudaMalloc(&s.d_frames, kSlotFrames * h->frame_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_hash, kSlotFrames * 32);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_quality, kSlotFrames * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaHostAlloc(&s.h_hash, kSlotFrames * 32, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc(&s.h_quality, kSlotFrames * sizeof(int32_t), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        // the big pinned frame buffer is allocated on first use (most videos never need slots 1, 2)
+    }
+    if (e != cudaSuccess) {
+        hasher_free(h);
+        return cuda_fail(e, "vpdq_b200_hasher_create");
+    }
+    *out = h;
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_hasher_push(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames) {
+    if (!h || n_frames < 0 || (n_frames > 0 && !h_frames)) {
+        set_error("hasher_push: invalid argument");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (g.rc) return g.rc;
+    for (int64_t f = 0; f < n_frames;) {
+        Slot& s = h->slots[h->cur];
+        if (s.filled == 0 && s.in_flight) {  // back-pressure: block until this slot's batch is done
+            int rc = slot_collect(h, s);
+            if (rc) return rc;
+        }
+        if (!s.h_frames) VPDQ_CUDA(cudaHostAlloc(&s.h_frames, kSlotFrames * h->frame_bytes, cudaHostAllocDefault));
+        int64_t take = kSlotFrames - s.filled;
+        if (take > n_frames - f) take = n_frames - f;
+        memcpy(s.h_frames + (size_t)s.filled * h->frame_bytes, h_frames + (size_t)f * h->frame_bytes,
+               (size_t)take * h->frame_bytes);
+        s.filled += (int)take;
+        f += take;
+        h->pushed += take;
+        if (s.filled == kSlotFrames) {
+            int rc = slot_submit(h, s);
+            if (rc) return rc;
+            h->cur = (h->cur + 1) % kSlots;
+        }
+    }
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_hasher_pushed(vpdq_b200_hasher* h, int64_t* n) {
+    if (!h || !n) return VPDQ_B200_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(h->mu);
+    *n = h->pushed;
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_hasher_finish(vpdq_b200_hasher* h, int quality_keep, uint8_t* h_hashes, int64_t cap, int64_t* n_kept,
+                            uint8_t* h_all_hashes, int32_t* h_all_quality) {
+    if (!h || !n_kept || cap < 0 || (cap > 0 && !h_hashes)) {
+        set_error("hasher_finish: invalid argument");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (g.rc) return g.rc;
+    // submit the partial batch, then drain the ring in submission order (oldest = slot after cur)
+    int rc = slot_submit(h, h->slots[h->cur]);
+    if (rc) return rc;
+    for (int k = 1; k <= kSlots; ++k) {
+        rc = slot_collect(h, h->slots[(h->cur + k) % kSlots]);
+        if (rc) return rc;
+    }
+    const int64_t n = h->pushed;
+    int64_t kept = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (h->quality[i] >= quality_keep) {
+            if (kept < cap) memcpy(h_hashes + kept * 32, h->hashes.data() + i * 32, 32);
+            ++kept;
+        }
+    if (h_all_hashes && n) memcpy(h_all_hashes, h->hashes.data(), (size_t)n * 32);
+    if (h_all_quality && n) memcpy(h_all_quality, h->quality.data(), (size_t)n * sizeof(int32_t));
+    *n_kept = kept;
+    h->hashes.clear();
+    h->quality.clear();
+    h->pushed = 0;
+    h->cur = 0;
+    if (kept > cap) {
+        set_error("hasher_finish: %lld hashes kept but capacity is %lld", (long long)kept, (long long)cap);
+        return VPDQ_B200_ERR_OVERFLOW;
+    }
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_hasher_destroy(vpdq_b200_hasher* h) {
+    if (!h) return VPDQ_B200_OK;
+    {
+        DeviceGuard g(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        hasher_free(h);
+    }
+    return VPDQ_B200_OK;
+}
+
+// ---- Hamming -----------------------------------------------------------------------------------------
+int vpdq_b200_hamming_scan_dev(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets, int64_t n_videos,
+                               const uint64_t* d_query, int n_query, int tolerance, uint64_t* d_qmask,
+                               int32_t* d_tcount, void* stream) {
+    if (n_db < 0 || n_videos < 0 || n_query < 0 || n_query > 64 || tolerance < 0) {
+        set_error("hamming_scan: invalid sizes (n_db=%lld n_videos=%lld n_query=%d, at most 64 query frames per call)",
+                  (long long)n_db, (long long)n_videos, n_query);
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (n_db == 0 || n_query == 0) return VPDQ_B200_OK;
+    if (!d_db || !d_query || !d_qmask || (!d_offsets && n_videos != n_db) || (d_offsets && n_videos < 1)) {
+        set_error("hamming_scan: NULL pointer or n_videos inconsistent with offsets");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (((uintptr_t)d_db & 31) || ((uintptr_t)d_query & 15)) {
+        set_error("hamming_scan: db must be 32-byte and query 16-byte aligned");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return hamming_scan_launch(d_db, n_db, d_offsets, n_videos, d_query, n_query, tolerance, d_qmask, d_tcount,
+                               (cudaStream_t)stream);
+}
+
+int vpdq_b200_hamming_pairs_dev(const uint64_t* d_q, int64_t n_q, const uint64_t* d_t, int64_t n_t, int tolerance,
+                                int skip_diagonal, uint32_t* d_any, uint64_t* d_pairs, int64_t cap,
+                                unsigned long long* d_count, void* stream) {
+    if (n_q < 0 || n_t < 0 || tolerance < 0 || cap < 0) {
+        set_error("hamming_pairs: invalid sizes");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (n_q == 0 || n_t == 0) return VPDQ_B200_OK;
+    if (!d_q || !d_t || !d_count || (cap > 0 && !d_pairs)) {
+        set_error("hamming_pairs: NULL pointer");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (((uintptr_t)d_q & 15) || ((uintptr_t)d_t & 15)) {
+        set_error("hamming_pairs: hash matrices must be 16-byte aligned");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return hamming_pairs_launch(d_q, n_q, d_t, n_t, tolerance, skip_diagonal, d_any, cap > 0 ? d_pairs : nullptr, cap,
+                                d_count, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ====================================================================================================
+// resident hash database (the brute-force replacement of the vp-tree, db/vptree.py)
+// ====================================================================================================
+struct vpdq_b200_db {
+    int device = 0;
+    int64_t n_db = 0, n_videos = 0;
+    uint64_t* d_db = nullptr;
+    int64_t* d_offsets = nullptr;
+    uint64_t* d_qmask = nullptr;  // [n_videos]
+    uint64_t* d_query = nullptr;  // [64][4]
+    uint64_t* h_qmask = nullptr;  // pinned
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+
+static void db_free(vpdq_b200_db* db) {
+    if (db->d_db) cudaFree(db->d_db);
+    if (db->d_offsets) cudaFree(db->d_offsets);
+    if (db->d_qmask) cudaFree(db->d_qmask);
+    if (db->d_query) cudaFree(db->d_query);
+    if (db->h_qmask) cudaFreeHost(db->h_qmask);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+extern "C" {
+
+int vpdq_b200_db_create(int device, const uint8_t* h_db, int64_t n_db, const int64_t* h_offsets, int64_t n_videos,
+                        vpdq_b200_db** out) {
+    if (!out) return VPDQ_B200_ERR_INVALID;
+    *out = nullptr;
+    if (n_db < 0 || n_videos < 0 || (n_db > 0 && !h_db) || (n_videos > 0 && !h_offsets)) {
+        set_error("db_create: invalid argument");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (n_videos > 0) {
+        if (h_offsets[0] != 0 || h_offsets[n_videos] != n_db) {
+            set_error("db_create: offsets must start at 0 and end at n_db");
+            return VPDQ_B200_ERR_INVALID;
+        }
+        for (int64_t v = 0; v < n_videos; ++v)
+            if (h_offsets[v] > h_offsets[v + 1]) {
+                set_error("db_create: offsets must be non-decreasing");
+                return VPDQ_B200_ERR_INVALID;
+            }
+    } else if (n_db != 0) {
+        set_error("db_create: frames without videos");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+    vpdq_b200_db* db = new (std::nothrow) vpdq_b200_db;
+    if (!db) return VPDQ_B200_ERR_NOMEM;
+    db->n_db = n_db;
+    db->n_videos = n_videos;
+    cudaError_t e = cudaGetDevice(&db->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_db, (size_t)(n_db > 0 ? n_db : 1) * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_offsets, (size_t)(n_videos + 1) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_qmask, (size_t)(n_videos > 0 ? n_videos : 1) * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_query, 64 * 32);
+    if (e == cudaSuccess)
+        e = cudaHostAlloc(&db->h_qmask, (size_t)(n_videos > 0 ? n_videos : 1) * sizeof(uint64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess && n_db > 0)
+        e = cudaMemcpyAsync(db->d_db, h_db, (size_t)n_db * 32, cudaMemcpyHostToDevice, db->stream);
+    if (e == cudaSuccess && n_videos > 0)
+        e = cudaMemcpyAsync(db->d_offsets, h_offsets, (size_t)(n_videos + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                            db->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+    if (e != cudaSuccess) {
+        db_free(db);
+        return cuda_fail(e, "vpdq_b200_db_create");
+    }
+    *out = db;
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_db_search(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_query, int tolerance,
+                        int32_t* h_matched) {
+    if (!db || n_query < 0 || tolerance < 0 || (n_query > 0 && !h_query) || (db->n_videos > 0 && !h_matched)) {
+        set_error("db_search: invalid argument");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(db->mu);
+    for (int64_t v = 0; v < db->n_videos; ++v) h_matched[v] = 0;
+    if (db->n_db == 0 || n_query == 0 || db->n_videos == 0) return VPDQ_B200_OK;
+    DeviceGuard g(db->device);
+    if (g.rc) return g.rc;
+    for (int64_t q0 = 0; q0 < n_query; q0 += 64) {
+        const int nq = (int)(n_query - q0 < 64 ? n_query - q0 : 64);
+        VPDQ_CUDA(cudaMemcpyAsync(db->d_query, h_query + q0 * 32, (size_t)nq * 32, cudaMemcpyHostToDevice, db->stream));
+        VPDQ_CUDA(cudaMemsetAsync(db->d_qmask, 0, (size_t)db->n_videos * sizeof(uint64_t), db->stream));
+        int rc = hamming_scan_launch(db->d_db, db->n_db, db->d_offsets, db->n_videos, db->d_query, nq, tolerance,
+                                     db->d_qmask, nullptr, db->stream);
+        if (rc) return rc;
+        VPDQ_CUDA(cudaMemcpyAsync(db->h_qmask, db->d_qmask, (size_t)db->n_videos * sizeof(uint64_t),
+                                  cudaMemcpyDeviceToHost, db->stream));
+        VPDQ_CUDA(cudaStreamSynchronize(db->stream));
+        for (int64_t v = 0; v < db->n_videos; ++v) h_matched[v] += __builtin_popcountll(db->h_qmask[v]);
+    }
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_db_destroy(vpdq_b200_db* db) {
+    if (!db) return VPDQ_B200_OK;
+    DeviceGuard g(db->device);
+    if (db->stream) cudaStreamSynchronize(db->stream);
+    db_free(db);
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_search_host(const uint8_t* h_db, int64_t n_db, const int64_t* h_offsets, int64_t n_videos,
+                          const uint8_t* h_query, int64_t n_query, int tolerance, int32_t* h_matched, int device) {
+    vpdq_b200_db* db = nullptr;
+    int rc = vpdq_b200_db_create(device, h_db, n_db, h_offsets, n_videos, &db);
+    if (rc) return rc;
+    rc = vpdq_b200_db_search(db, h_query, n_query, tolerance, h_matched);
+    vpdq_b200_db_destroy(db);
+    return rc;
+}
+
+int vpdq_b200_match_hash_host(const uint8_t* h_q, int64_t n_q, const uint8_t* h_t, int64_t n_t, int tolerance,
+                              double* similarity, int device) {
+    if (!similarity || n_q < 0 || n_t < 0) {
+        set_error("match_hash: invalid argument");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    *similarity = 0.0;
+    if (n_q == 0 || n_t == 0) return VPDQ_B200_OK;  // an empty hash is similar to nothing (DedupeDB.py:555-557)
+    const int64_t off[2] = {0, n_t};
+    int32_t matched = 0;
+    int rc = vpdq_b200_search_host(h_t, n_t, off, 1, h_q, n_q, tolerance, &matched, device);
+    if (rc) return rc;
+    *similarity = (100.0 * (double)matched) / (double)n_q;
+    return VPDQ_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+// hamming_kernels.cu -- brute-force Hamming similarity over packed 256-bit PDQ hashes (sm_100a).
+//
+// Replaces hvdaccelerators.vpdq.matchHash / matchHashBytes (reference call sites
+// vpdqpy/vpdqpy.py:56 and db/vptree.py:31) and, as ONE pass over the hash database, the
+// calculate_distance calls the vp-tree issues per visited node (db/vptree.py:737).
+//
+// Frame match:  popcount(q ^ t) <= tol  on 4 x u64.  Integer work only: no
+// tensor cores, no floating point.
+//
+//   k_hamming_scan   streaming regime (the reference's real call pattern: one query video against the
+//                    whole DB).  One thread per DB hash, one 256-bit load (LDG.E.256) per hash, the
+//                    <= 64 query hashes broadcast from shared memory.  HBM-bound for small n_query:
+//                    algorithmic traffic = 32 B per DB hash.
+//   k_hamming_pairs  all-pairs regime (1M x 1M).  The DB is L2-resident there and the kernel is bound
+//                    by POPC issue, so the inner loop is a 96-bit prefilter (3 POPC per pair): a pair
+//                    whose first 96 bits already differ in > tol places cannot match; survivors
+//                    (~4e-4 of random pairs) take the exact 256-bit path.
+#include <cuda_pipeline.h>
+
+#include "common.cuh"
+
+namespace vpdq {
+
+__device__ __forceinline__ void ld256(const uint64_t* p, uint32_t (&w)[8]) {
+    uint64_t a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(p));
+    w[0] = (uint32_t)a; w[1] = (uint32_t)(a >> 32);
+    w[2] = (uint32_t)b; w[3] = (uint32_t)(b >> 32);
+    w[4] = (uint32_t)c; w[5] = (uint32_t)(c >> 32);
+    w[6] = (uint32_t)d; w[7] = (uint32_t)(d >> 32);
+}
+
+// video owning frame idx: the v with offsets[v] <= idx < offsets[v+1]
+__device__ __forceinline__ int64_t video_of(const int64_t* __restrict__ offsets, int64_t n_videos, int64_t idx) {
+    int64_t lo = 0, hi = n_videos;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= idx)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// streaming scan
+// ---------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanUnroll = 2;
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_hamming_scan(const uint64_t* __restrict__ db, int64_t n_db, const int64_t* __restrict__ offsets,
+                   int64_t n_videos, const uint64_t* __restrict__ query, int n_query, int tol,
+                   unsigned long long* __restrict__ qmask, int32_t* __restrict__ tcount) {
+    __shared__ uint4 q_s[64 * 2];
+    for (int e = threadIdx.x; e < n_query * 2; e += kScanThreads)
+        q_s[e] = __ldg(reinterpret_cast<const uint4*>(query) + e);
+    __syncthreads();
+
+    constexpr int64_t kTile = (int64_t)kScanThreads * kScanUnroll;
+    const int64_t n_tiles = (n_db + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * kTile + threadIdx.x;
+        uint32_t h[kScanUnroll][8];
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kScanThreads;
+            if (idx < n_db) ld256(db + 4 * idx, h[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kScanUnroll; ++u) {
+            const int64_t idx = base + (int64_t)u * kScanThreads;
+            if (idx >= n_db) continue;
+            unsigned long long mask = 0ull;
+            for (int qi = 0; qi < n_query; ++qi) {
+                const uint4 a = q_s[2 * qi], b = q_s[2 * qi + 1];
+                int d = __popc(h[u][0] ^ a.x) + __popc(h[u][1] ^ a.y) + __popc(h[u][2] ^ a.z) +
+                        __popc(h[u][3] ^ a.w);
+                if (d <= tol) {
+                    d += __popc(h[u][4] ^ b.x) + __popc(h[u][5] ^ b.y) + __popc(h[u][6] ^ b.z) +
+                         __popc(h[u][7] ^ b.w);
+                    if (d <= tol) mask |= 1ull << qi;
+                }
+            }
+            if (mask) {
+                const int64_t v = offsets ? video_of(offsets, n_videos, idx) : idx;
+                atomicOr(qmask + v, mask);
+                if (tcount) atomicAdd(tcount + v, 1);
+            }
+        }
+    }
+}
+
+int hamming_scan_launch(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets, int64_t n_videos,
+                        const uint64_t* d_query, int n_query, int tol, uint64_t* d_qmask, int32_t* d_tcount,
+                        cudaStream_t stream) {
+    if (n_db == 0 || n_query == 0) return VPDQ_B200_OK;
+    int dev = 0, sms = 148;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    VPDQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t kTile = (int64_t)kScanThreads * kScanUnroll;
+    const int64_t n_tiles = (n_db + kTile - 1) / kTile;
+    const int64_t max_grid = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM, persistent
+    const unsigned grid = (unsigned)(n_tiles < max_grid ? n_tiles : max_grid);
+    k_hamming_scan<<<grid, kScanThreads, 0, stream>>>(d_db, n_db, d_offsets, n_videos, d_query, n_query, tol,
+                                                      reinterpret_cast<unsigned long long*>(d_qmask), d_tcount);
+    VPDQ_CUDA(cudaGetLastError());
+    return VPDQ_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// all pairs
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 256;
+constexpr int kPairQR = 8;                            // queries per thread (96-bit prefixes in registers)
+constexpr int kPairQTile = kPairThreads * kPairQR;    // 2048 queries per CTA
+constexpr int kPairTTile = 1024;                      // target prefixes per shared-memory stage (16 KB)
+
+__device__ __forceinline__ int full_distance(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b) {
+    return __popcll(__ldg(a) ^ __ldg(b)) + __popcll(__ldg(a + 1) ^ __ldg(b + 1)) +
+           __popcll(__ldg(a + 2) ^ __ldg(b + 2)) + __popcll(__ldg(a + 3) ^ __ldg(b + 3));
+}
+
+__global__ void __launch_bounds__(kPairThreads)
+    k_hamming_pairs(const uint64_t* __restrict__ qs, int64_t n_q, const uint64_t* __restrict__ ts, int64_t n_t,
+                    int64_t t_chunk, int tol, int skip_diagonal, uint32_t* __restrict__ any,
+                    unsigned long long* __restrict__ pairs, int64_t cap, unsigned long long* __restrict__ count) {
+    __shared__ uint4 tile[2][kPairTTile];  // first 128 bits of each target hash
+
+    const int64_t q0 = (int64_t)blockIdx.x * kPairQTile + threadIdx.x;
+    uint32_t q[kPairQR][3];
+#pragma unroll
+    for (int r = 0; r < kPairQR; ++r) {
+        const int64_t i = q0 + (int64_t)r * kPairThreads;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < n_q) v = __ldg(reinterpret_cast<const uint4*>(qs + 4 * i));
+        q[r][0] = v.x; q[r][1] = v.y; q[r][2] = v.z;
+    }
+
+    const int64_t t_begin = (int64_t)blockIdx.y * t_chunk;
+    const int64_t t_end = (t_begin + t_chunk < n_t) ? (t_begin + t_chunk) : n_t;
+    if (t_begin >= t_end) return;
+    const int n_stage = (int)((t_end - t_begin + kPairTTile - 1) / kPairTTile);
+
+    auto prefetch = [&](int s) {
+        const int64_t base = t_begin + (int64_t)s * kPairTTile;
+#pragma unroll
+        for (int e = 0; e < kPairTTile / kPairThreads; ++e) {
+            const int slot = e * kPairThreads + threadIdx.x;
+            const int64_t j = base + slot;
+            if (j < t_end) __pipeline_memcpy_async(&tile[s & 1][slot], ts + 4 * j, 16);
+        }
+        __pipeline_commit();
+    };
+
+    prefetch(0);
+    for (int s = 0; s < n_stage; ++s) {
+        if (s + 1 < n_stage) prefetch(s + 1);
+        else __pipeline_commit();
+        __pipeline_wait_prior(1);
+        __syncthreads();
+
+        const int64_t base = t_begin + (int64_t)s * kPairTTile;
+        const int cnt = (int)((t_end - base < kPairTTile) ? (t_end - base) : kPairTTile);
+        const uint4* tl = tile[s & 1];
+#pragma unroll 2
+        for (int tt = 0; tt < cnt; ++tt) {
+            const uint4 tp = tl[tt];  // broadcast read
+            int best = 1 << 20;
+#pragma unroll
+            for (int r = 0; r < kPairQR; ++r) {
+                const int d = __popc(q[r][0] ^ tp.x) + __popc(q[r][1] ^ tp.y) + __popc(q[r][2] ^ tp.z);
+                best = min(best, d);
+            }
+            if (best <= tol) {  // rare: some query's 96-bit prefix is within tol of this target
+                const int64_t j = base + tt;
+#pragma unroll
+                for (int r = 0; r < kPairQR; ++r) {
+                    const int d = __popc(q[r][0] ^ tp.x) + __popc(q[r][1] ^ tp.y) + __popc(q[r][2] ^ tp.z);
+                    const int64_t i = q0 + (int64_t)r * kPairThreads;
+                    if (d <= tol && i < n_q && !(skip_diagonal && i == j) &&
+                        full_distance(qs + 4 * i, ts + 4 * j) <= tol) {
+                        if (any) atomicOr(any + (i >> 5), 1u << (i & 31));
+                        const unsigned long long pos = atomicAdd(count, 1ull);
+                        if (pairs && (int64_t)pos < cap) pairs[pos] = ((unsigned long long)i << 32) | (unsigned long long)j;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with tile[s & 1] before it is refilled at s + 2
+    }
+}
+
+int hamming_pairs_launch(const uint64_t* d_q, int64_t n_q, const uint64_t* d_t, int64_t n_t, int tol,
+                         int skip_diagonal, uint32_t* d_any, uint64_t* d_pairs, int64_t cap,
+                         unsigned long long* d_count, cudaStream_t stream) {
+    if (n_q == 0 || n_t == 0) return VPDQ_B200_OK;
+    if (n_q >= (1ll << 32) || n_t >= (1ll << 32)) {
+        set_error("hamming_pairs: at most 2^32-1 hashes per side");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    int dev = 0, sms = 148;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    VPDQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t q_tiles = (n_q + kPairQTile - 1) / kPairQTile;
+    // split the targets so that the grid holds >= 4 CTAs per SM, in whole shared-memory stages
+    int64_t want = ((int64_t)sms * 4 + q_tiles - 1) / q_tiles;
+    const int64_t t_stages = (n_t + kPairTTile - 1) / kPairTTile;
+    if (want > t_stages) want = t_stages;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    const int64_t t_chunk = ((t_stages + want - 1) / want) * kPairTTile;
+    const int64_t t_splits = (n_t + t_chunk - 1) / t_chunk;
+    dim3 grid((unsigned)q_tiles, (unsigned)t_splits);
+    k_hamming_pairs<<<grid, kPairThreads, 0, stream>>>(d_q, n_q, d_t, n_t, t_chunk, tol, skip_diagonal, d_any,
+                                                       reinterpret_cast<unsigned long long*>(d_pairs), cap, d_count);
+    VPDQ_CUDA(cudaGetLastError());
+    return VPDQ_B200_OK;
+}
+
+}  // namespace vpdq

@@ -1,0 +1,126 @@
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is used here only as the device-memory container and stream provider (and by ``dist.py`` for
+NCCL); every operation is one call through the C ABI (``*_dev`` functions of include/vpdq_b200.h) on the
+caller's current CUDA stream.  Nothing here synchronises unless it has to return a Python number.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _ffi
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+_scratch: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def pdq_scratch(n_frames: int, device: torch.device) -> torch.Tensor:
+    """Cached scratch for the PDQ passes (sized by the library; reused across calls on one stream)."""
+    need = C.c_size_t(0)
+    _ffi.check(_ffi.lib().vpdq_b200_pdq_scratch_bytes(int(n_frames), C.byref(need)))
+    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < need.value:
+        buf = torch.empty(need.value, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def hash_frames(frames: torch.Tensor, *, stages: bool = False):
+    """frames: [n, 512, 512, 3] (RGB24) or [n, 512, 512] (gray == R=G=B) uint8 CUDA tensor ->
+    (hashes [n, 32] uint8, quality [n] int32) on the same device, unfiltered.
+    stages=True also returns (A [n, 64, 64] f32 decimated plane, B [n, 16, 16] f32 DCT)."""
+    frames = _need_cuda(frames, "frames", torch.uint8)
+    if frames.dim() == 4 and frames.shape[3] == 3:
+        ch = 3
+    elif frames.dim() == 3:
+        ch = 1
+    else:
+        raise ValueError("frames must be [n, 512, 512, 3] or [n, 512, 512]")
+    n, h, w = frames.shape[:3]
+    dev = frames.device
+    hashes = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    quality = torch.empty((n,), dtype=torch.int32, device=dev)
+    a64 = torch.empty((n, 64, 64), dtype=torch.float32, device=dev) if stages else None
+    b16 = torch.empty((n, 16, 16), dtype=torch.float32, device=dev) if stages else None
+    with torch.cuda.device(dev):
+        scratch = pdq_scratch(n, dev)
+        _ffi.check(_ffi.lib().vpdq_b200_pdq_stages_dev(
+            frames.data_ptr(), ch, n, w, h, hashes.data_ptr(), quality.data_ptr(),
+            a64.data_ptr() if stages else None, b16.data_ptr() if stages else None,
+            scratch.data_ptr(), scratch.numel(), _stream_ptr()))
+    if stages:
+        return hashes, quality, a64, b16
+    return hashes, quality
+
+
+def _as_hash_matrix(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[n, 32] uint8 or [n, 4] int64 -> contiguous CUDA tensor, 32-byte rows"""
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype == torch.uint8 and t.dim() == 2 and t.shape[1] == 32:
+        return t.contiguous()
+    if t.dtype == torch.int64 and t.dim() == 2 and t.shape[1] == 4:
+        return t.contiguous()
+    raise ValueError(f"{name} must be [n, 32] uint8 or [n, 4] int64")
+
+
+def hamming_scan(db: torch.Tensor, query: torch.Tensor, offsets: torch.Tensor | None = None, tolerance: int = 31,
+                 *, reverse_counts: bool = False):
+    """One streaming pass of <= 64 query frames over the database.
+    -> qmask [n_videos] int64 (bit i = query frame i matched in video v) and, if reverse_counts,
+       tcount [n_videos] int32 (# frames of video v that matched some query frame)."""
+    db = _as_hash_matrix(db, "db")
+    query = _as_hash_matrix(query, "query")
+    n_db, n_q = db.shape[0], query.shape[0]
+    if n_q > 64:
+        raise ValueError("at most 64 query frames per scan; chunk the query")
+    if offsets is not None:
+        offsets = _need_cuda(offsets, "offsets", torch.int64)
+        n_videos = offsets.numel() - 1
+    else:
+        n_videos = n_db
+    dev = db.device
+    qmask = torch.zeros((n_videos,), dtype=torch.int64, device=dev)
+    tcount = torch.zeros((n_videos,), dtype=torch.int32, device=dev) if reverse_counts else None
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.lib().vpdq_b200_hamming_scan_dev(
+            db.data_ptr(), n_db, offsets.data_ptr() if offsets is not None else None, n_videos, query.data_ptr(),
+            n_q, int(tolerance), qmask.data_ptr(), tcount.data_ptr() if reverse_counts else None, _stream_ptr()))
+    return (qmask, tcount) if reverse_counts else qmask
+
+
+def hamming_pairs(q: torch.Tensor, t: torch.Tensor, tolerance: int = 31, *, skip_diagonal: bool = False,
+                  capacity: int = 1 << 20, want_bitmap: bool = True):
+    """Brute-force all pairs.  -> (count: int, pairs [min(count, capacity), 2] int64 (unordered),
+    any_bitmap [(n_q+31)//32] int32 or None).  Synchronises to read the count."""
+    q = _as_hash_matrix(q, "q")
+    t = _as_hash_matrix(t, "t")
+    dev = q.device
+    n_q, n_t = q.shape[0], t.shape[0]
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    pairs = torch.empty((max(1, capacity),), dtype=torch.int64, device=dev)
+    bitmap = torch.zeros(((n_q + 31) // 32,), dtype=torch.int32, device=dev) if want_bitmap else None
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.lib().vpdq_b200_hamming_pairs_dev(
+            q.data_ptr(), n_q, t.data_ptr(), n_t, int(tolerance), int(bool(skip_diagonal)),
+            bitmap.data_ptr() if want_bitmap else None, pairs.data_ptr(), int(capacity), count.data_ptr(),
+            _stream_ptr()))
+    n = int(count.item())
+    packed = pairs[: min(n, capacity)]
+    out = torch.stack(((packed >> 32) & 0xFFFFFFFF, packed & 0xFFFFFFFF), dim=1)
+    return n, out, bitmap

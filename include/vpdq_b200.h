@@ -1,0 +1,156 @@
+/*
+ * vpdq_b200.h -- C ABI of libvpdq_b200.so: the B200 (sm_100a) replacement for the native half of
+ * hydrus-video-deduplicator's hot path.
+ *
+ * In the reference every entry below is a call into the third-party C++ wheel
+ * `hvdaccelerators.vpdq` (pyproject.toml:36); the citations name the reference-side call site each
+ * entry point replaces (paths relative to /root/reference/src/hydrusvideodeduplicator/).
+ *
+ * Conventions
+ *   - plain C, no exceptions across the boundary; every function returns VPDQ_B200_OK (0) or a
+ *     negative vpdq_b200_status; vpdq_b200_last_error() returns a thread-local message.
+ *   - "_dev" entry points take DEVICE pointers, are stream-ordered on `stream` (a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream), never allocate and never synchronise.
+ *   - "_host" entry points and the hasher handle take HOST pointers, own their staging buffers and
+ *     include the host<->device copies (this is what the reference's Python binds to).
+ *   - a PDQ hash is 32 bytes in "native PDQ order": bit k = 16*i + j of the 16x16 DCT sign matrix
+ *     lives in byte k>>3, bit k&7 (DedupeDB.py:538-544); hash matrices are row-major [n][32] bytes,
+ *     equivalently [n][4] little-endian uint64 -- exactly the reference's phash BLOB (dedup.py:77).
+ *   - frames are 512 x 512, row-major, RGB24 interleaved (channels = 3; vpdqpy.py:90-95,118) or
+ *     8-bit gray (channels = 1, DEFINED as the RGB frame R=G=B=L).
+ *   - there is NO CPU implementation behind any of these: without a CUDA device they fail with
+ *     VPDQ_B200_ERR_CUDA.
+ */
+#ifndef VPDQ_B200_H
+#define VPDQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VPDQ_B200_API __attribute__((visibility("default")))
+#else
+#define VPDQ_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vpdq_b200_status {
+    VPDQ_B200_OK = 0,
+    VPDQ_B200_ERR_INVALID = -1,     /* bad argument (NULL, negative size, wrong frame size, ...)  */
+    VPDQ_B200_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed / no device           */
+    VPDQ_B200_ERR_NOMEM = -3,       /* host or device allocation failed                           */
+    VPDQ_B200_ERR_UNSUPPORTED = -4, /* e.g. frame dimensions other than 512 x 512                 */
+    VPDQ_B200_ERR_OVERFLOW = -5     /* an output list was larger than the capacity supplied       */
+} vpdq_b200_status;
+
+#define VPDQ_B200_FRAME_DIM 512
+#define VPDQ_B200_HASH_BYTES 32          /* VpdqHash.bytesPerPdqHash, dedup.py:83-84               */
+#define VPDQ_B200_QUALITY_KEEP 31        /* finish() keeps quality >= 31, DedupeDB.py:550-553      */
+#define VPDQ_B200_DEFAULT_TOLERANCE 31   /* vpdqpy.py:53, vptree.py:31                             */
+
+VPDQ_B200_API const char* vpdq_b200_last_error(void);
+VPDQ_B200_API int vpdq_b200_abi_version(void);
+VPDQ_B200_API int vpdq_b200_device_count(int* count);
+/* the 16 x 64 fp32 DCT table the kernels use (host copy; bit-identical to the oracle's) */
+VPDQ_B200_API int vpdq_b200_dct_matrix(float* out /* [16*64] */);
+
+/* ------------------------------------------------------------------------------------------------
+ * PDQ frame hashing.  Replaces the work behind VideoHasher.hash_frame (vpdqpy.py:118):
+ * RGB->luma, 2x Jarosz box blur, decimate to 64x64, quality metric, 64->16 DCT, median, 256 bits.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* bytes of device scratch vpdq_b200_pdq_hash_frames_dev needs for `n_frames` frames */
+VPDQ_B200_API int vpdq_b200_pdq_scratch_bytes(int64_t n_frames, size_t* bytes);
+
+/* d_frames [n][512][512][channels] u8 -> d_hashes [n][32] u8, d_quality [n] i32 (0..100).
+ * No quality filtering here: the caller (finish()) drops frames. */
+VPDQ_B200_API int vpdq_b200_pdq_hash_frames_dev(const uint8_t* d_frames, int channels, int64_t n_frames, int width, int height,
+                                  uint8_t* d_hashes, int32_t* d_quality, void* d_scratch, size_t scratch_bytes,
+                                  void* stream);
+
+/* Debug/parity aid: additionally returns the decimated 64x64 plane ([n][64][64] f32) and the
+ * 16x16 DCT ([n][16][16] f32); either may be NULL. */
+VPDQ_B200_API int vpdq_b200_pdq_stages_dev(const uint8_t* d_frames, int channels, int64_t n_frames, int width, int height,
+                             uint8_t* d_hashes, int32_t* d_quality, float* d_a64, float* d_b16, void* d_scratch,
+                             size_t scratch_bytes, void* stream);
+
+/* One-shot host call: h_frames -> h_hashes/h_quality, copies included (pinned or pageable memory). */
+VPDQ_B200_API int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_t n_frames, int width, int height,
+                                   uint8_t* h_hashes, int32_t* h_quality, int device);
+
+/* Streaming hasher handle == hvdaccelerators.vpdq.VideoHasher
+ *   create  <- vpdq.VideoHasher(average_fps, width, height, num_threads)        vpdqpy.py:113
+ *   push    <- hasher.hash_frame(bytes)   (blocks while the staging ring is full) vpdqpy.py:115-118
+ *   finish  <- hasher.finish(): hashes of the frames with quality >= 31, in push order  vpdqpy.py:119
+ * `num_threads` is accepted for signature compatibility and ignored (the GPU is the pool). */
+typedef struct vpdq_b200_hasher vpdq_b200_hasher;
+VPDQ_B200_API int vpdq_b200_hasher_create(int device, int width, int height, int channels, int num_threads,
+                            vpdq_b200_hasher** out);
+VPDQ_B200_API int vpdq_b200_hasher_push(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames);
+/* total frames pushed so far (upper bound for finish's capacity) */
+VPDQ_B200_API int vpdq_b200_hasher_pushed(vpdq_b200_hasher* h, int64_t* n);
+/* Writes kept hashes (quality >= quality_keep) to h_hashes [cap][32]; *n_kept = number kept.
+ * h_all_hashes [pushed][32] / h_all_quality [pushed] (optional, may be NULL) receive the unfiltered
+ * results.  The hasher is reset and reusable afterwards. */
+VPDQ_B200_API int vpdq_b200_hasher_finish(vpdq_b200_hasher* h, int quality_keep, uint8_t* h_hashes, int64_t cap, int64_t* n_kept,
+                            uint8_t* h_all_hashes, int32_t* h_all_quality);
+VPDQ_B200_API int vpdq_b200_hasher_destroy(vpdq_b200_hasher* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hamming similarity.  Replaces vpdq.matchHash (vpdqpy.py:56), vpdq.matchHashBytes (vptree.py:31)
+ * and, as one brute-force pass, the calculate_distance storm under VpTreeManager.search_file
+ * (vptree.py:664-815, 865-902).  Frame match: popcount(q ^ t) <= tolerance.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Streaming scan of a hash database against ONE query video (<= 64 frames per call).
+ *   d_db      [n_db][4] u64        database frame hashes, videos stored contiguously
+ *   d_offsets [n_videos + 1] i64   CSR: video v owns frames d_offsets[v] .. d_offsets[v+1]-1
+ *                                  (NULL: every frame is its own video, n_videos must equal n_db)
+ *   d_query   [n_query][4] u64
+ *   d_qmask   [n_videos] u64  OUT  bit i set  <=>  query frame i matches >= 1 frame of video v
+ *                                  (popcount = numerator of matchHash(query, video v)); the call ORs
+ *                                  into it, zero it first (cudaMemsetAsync) for a fresh scan
+ *   d_tcount  [n_videos] i32  OUT  (optional) # frames of video v matching >= 1 query frame
+ *                                  (numerator of the reverse direction matchHash(video v, query)); adds */
+VPDQ_B200_API int vpdq_b200_hamming_scan_dev(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets, int64_t n_videos,
+                               const uint64_t* d_query, int n_query, int tolerance, uint64_t* d_qmask,
+                               int32_t* d_tcount, void* stream);
+
+/* Brute-force all pairs between two hash sets (self-join when both are the same buffer).
+ *   d_any   [(n_q + 31) / 32] u32  OUT (optional) bit i: query i has >= 1 match ("candidate bitmap"); ORs
+ *   d_pairs [cap] u64              OUT (optional) (i << 32) | j for every match, unordered
+ *   d_count [1] u64                OUT total number of matches found (may exceed cap; adds)
+ *   skip_diagonal != 0 ignores i == j (self-join). */
+VPDQ_B200_API int vpdq_b200_hamming_pairs_dev(const uint64_t* d_q, int64_t n_q, const uint64_t* d_t, int64_t n_t, int tolerance,
+                                int skip_diagonal, uint32_t* d_any, uint64_t* d_pairs, int64_t cap,
+                                unsigned long long* d_count, void* stream);
+
+/* vpdq.matchHash / matchHashBytes with host buffers: *similarity = 100 * matched_q / n_q as a double;
+ * 0.0 when either side is empty (DedupeDB.py:555-557).  n_q, n_t in frames. */
+VPDQ_B200_API int vpdq_b200_match_hash_host(const uint8_t* h_q, int64_t n_q, const uint8_t* h_t, int64_t n_t, int tolerance,
+                              double* similarity, int device);
+
+/* Resident hash database: the brute-force replacement of the vp-tree index (db/vptree.py).  The DB
+ * (the phash BLOBs of shape_perceptual_hashes, DedupeDB.py:159-180, concatenated; video v owns frames
+ * h_offsets[v] .. h_offsets[v+1]-1) is copied to HBM once; each search is one streaming pass.
+ *   search  <- the calculate_distance storm under VpTreeManager.search_file (vptree.py:865-902):
+ *              h_matched[v] = # query frames with >= 1 match in video v, so that
+ *              matchHashBytes(query, video v) = 100.0 * h_matched[v] / n_query  (vptree.py:31). */
+typedef struct vpdq_b200_db vpdq_b200_db;
+VPDQ_B200_API int vpdq_b200_db_create(int device, const uint8_t* h_db, int64_t n_db, const int64_t* h_offsets, int64_t n_videos,
+                        vpdq_b200_db** out);
+VPDQ_B200_API int vpdq_b200_db_search(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_query, int tolerance,
+                        int32_t* h_matched /* [n_videos] */);
+VPDQ_B200_API int vpdq_b200_db_destroy(vpdq_b200_db* db);
+
+/* One-shot form of the above (creates, searches, destroys).  Any n_query (chunks of 64 inside). */
+VPDQ_B200_API int vpdq_b200_search_host(const uint8_t* h_db, int64_t n_db, const int64_t* h_offsets, int64_t n_videos,
+                          const uint8_t* h_query, int64_t n_query, int tolerance, int32_t* h_matched, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPDQ_B200_H */

@@ -1,0 +1,111 @@
+"""Pins the CPU oracle against every known-answer the reference holds for the hot path
+(SURVEY.md 8c): golden frame hashes (tests/unit_tests/test_vpdqpy.py:105-128), the similarity groups
+(test_vpdqpy.py:131-145) and the acceptance run's pair count (tests/acceptance_tests/test_main_vcr.py:64-66).
+CPU only."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from hydrus_video_deduplicator_b200.vpdqpy.vpdqpy import point_resize_rgb
+from tests import synth
+
+
+def _golden_hashes(golden_dir: Path) -> dict[str, bytes]:
+    return {p.name[:-4]: bytes.fromhex(p.read_text().strip()) for p in sorted((golden_dir / "video_hashes").glob("*.txt"))}
+
+
+@pytest.fixture(scope="module")
+def gif_frames_512(golden_dir):
+    native = np.load(golden_dir / "bbb_gif_frames.npz")["frames"]  # [10, 360, 640, 3]
+    return np.stack([point_resize_rgb(f) for f in native])
+
+
+def test_gif_known_answer_is_bit_exact(golden_dir, gif_frames_512):
+    """10/10 frame hashes of S01_Big_Buck_Bunny_360_10s.gif, 2560/2560 bits."""
+    hashes, quality = oracle.pdq_hash_frames(gif_frames_512)
+    gold = _golden_hashes(golden_dir)["S01_Big_Buck_Bunny_360_10s.gif"]
+    assert hashes.tobytes() == gold
+    assert (quality == 100).all()
+    assert oracle.video_hash(gif_frames_512) == gold
+
+
+def test_threaded_batch_equals_serial(gif_frames_512):
+    a = oracle.pdq_hash_frames(gif_frames_512, nthreads=1)
+    b = oracle.pdq_hash_frames(gif_frames_512, nthreads=4)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_golden_hashes_have_popcount_128(golden_dir):
+    for name, blob in _golden_hashes(golden_dir).items():
+        bits = np.unpackbits(np.frombuffer(blob, np.uint8).reshape(-1, 32), axis=1).sum(axis=1)
+        assert (bits == 128).all(), name
+
+
+def test_similarity_groups_on_golden_hashes(golden_dir):
+    """test_vpdqpy.py:131-145: same SXX_ prefix <=> is_similar at the default threshold 75."""
+    gold = _golden_hashes(golden_dir)
+    for a, ha in gold.items():
+        for b, hb in gold.items():
+            if a == b:
+                continue
+            similar, sim = oracle.is_similar(ha, hb)
+            assert 0.0 <= sim <= 100.0
+            assert similar == (a.split("_")[0] == b.split("_")[0]), (a, b, sim)
+
+
+def test_acceptance_pair_count(golden_dir):
+    """The VCR acceptance run (6 Big Buck Bunny files, CLI threshold 50) ends with 15 potential pairs."""
+    gold = _golden_hashes(golden_dir)
+    bbb = [h for n, h in gold.items() if n.startswith("S01_")]
+    assert len(bbb) == 6
+    radius = (100 - int(50.0)) + 1  # vptree.py:22-25
+    directed = sum(len([1 for v, d in oracle.search_file(bbb, i, radius) if v != i]) for i in range(6))
+    assert directed // 2 == 15  # dedup.py:502
+
+
+def test_match_semantics():
+    rng = np.random.default_rng(5)
+    h = synth.random_balanced_hashes(4, rng)
+    near = np.stack([synth.flip_bits(h[0], 30, rng), synth.flip_bits(h[1], 32, rng)])
+    assert oracle.match_hash(h[:2], near) == 50.0  # d=30 matches, d=32 does not
+    assert oracle.match_hash(b"", h) == 0.0 and oracle.match_hash(h, b"") == 0.0  # DedupeDB.py:555-557
+    assert oracle.calculate_distance(h, h) == 1 and oracle.calculate_distance(h[:1], h[1:2]) == 101
+    d31 = synth.flip_bits(h[2], 31, rng)
+    assert oracle.match_hash(h[2:3], d31.reshape(1, 32), 31) == 100.0  # comparator is <= tol
+    assert oracle.match_hash(h[2:3], d31.reshape(1, 32), 30) == 0.0
+
+
+def test_degenerate_frames():
+    black = np.zeros((1, 512, 512, 3), np.uint8)
+    h, q = oracle.pdq_hash_frames(black)
+    assert h.tobytes() == bytes(32) and q[0] == 0
+    assert oracle.video_hash(black) == b""  # quality < 31 -> dropped
+    gray = np.full((1, 512, 512, 3), 128, np.uint8)
+    _, q = oracle.pdq_hash_frames(gray)
+    assert q[0] == 0
+
+
+def test_gray_is_rgb_with_equal_channels():
+    g = synth.synth_frames(3, seed=11, channels=1)
+    rgb = np.repeat(g[..., None], 3, axis=3)
+    a = oracle.pdq_hash_frames(g)
+    b = oracle.pdq_hash_frames(rgb)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_synthetic_config0():
+    """BASELINE config 0 in miniature: planted noisy copies are found, unrelated videos are not."""
+    base = synth.synth_frames(12, seed=3)
+    vids = [base[0:4], base[4:8], base[8:12]]
+    vids += [synth.noisy_copy(v, seed=100 + i) for i, v in enumerate(vids)]
+    hashes = [oracle.video_hash(v) for v in vids]
+    for i in range(6):
+        for j in range(6):
+            if i == j or not hashes[i] or not hashes[j]:
+                continue
+            similar, _ = oracle.is_similar(hashes[i], hashes[j])
+            assert similar == (i % 3 == j % 3), (i, j)

@@ -1,0 +1,134 @@
+"""GPU parity of the PDQ frame-hash path against the CPU oracle (bit-exact: hashes, quality, and the
+fp32 intermediates).  Every call goes through the C ABI (libvpdq_b200.so)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import oracle
+from hydrus_video_deduplicator_b200 import vpdq
+from hydrus_video_deduplicator_b200.vpdqpy.vpdqpy import point_resize_rgb
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_dev():
+    import torch
+
+    return torch, torch.device("cuda", 0)
+
+
+def _gpu_hash(torch, dev, frames, stages=False):
+    from hydrus_video_deduplicator_b200 import device
+
+    out = device.hash_frames(torch.from_numpy(frames).to(dev), stages=stages)
+    torch.cuda.synchronize()
+    return tuple(o.cpu().numpy() for o in out)
+
+
+def test_gif_known_answer_on_gpu(golden_dir, torch_dev):
+    torch, dev = torch_dev
+    native = np.load(golden_dir / "bbb_gif_frames.npz")["frames"]
+    frames = np.stack([point_resize_rgb(f) for f in native])
+    hashes, quality = _gpu_hash(torch, dev, frames)
+    gold = bytes.fromhex((golden_dir / "video_hashes" / "S01_Big_Buck_Bunny_360_10s.gif.txt").read_text().strip())
+    assert hashes.tobytes() == gold
+    assert (quality == 100).all()
+
+
+def test_stages_bit_exact_vs_oracle(torch_dev):
+    """The 64x64 decimated plane and the 16x16 DCT must match the oracle to the last bit: this is what
+    pins the fp32 operation order (no FMA contraction, sequential running sums)."""
+    torch, dev = torch_dev
+    frames = synth.synth_frames(9, seed=21)
+    hashes, quality, a64, b16 = _gpu_hash(torch, dev, frames, stages=True)
+    for k in range(len(frames)):
+        h, q, a, b = oracle.pdq_stages(frames[k])
+        assert a64[k].tobytes() == a.tobytes(), f"decimated plane differs, frame {k}"
+        assert b16[k].tobytes() == b.tobytes(), f"DCT differs, frame {k}"
+        assert hashes[k].tobytes() == h.tobytes() and quality[k] == q
+
+
+@pytest.mark.parametrize("channels", [3, 1])
+def test_synthetic_frames_bit_exact(torch_dev, channels):
+    torch, dev = torch_dev
+    n = 300 if channels == 3 else 90  # > one internal chunk (256) for RGB
+    frames = synth.synth_frames(n, seed=7, channels=channels)
+    hashes, quality = _gpu_hash(torch, dev, frames)
+    ref_h, ref_q = oracle.pdq_hash_frames(frames, nthreads=8)
+    bad = np.flatnonzero((hashes != ref_h).any(axis=1) | (quality != ref_q))
+    assert bad.size == 0, f"{bad.size} of {n} frames differ, first {bad[:5]}"
+
+
+def test_degenerate_frames(torch_dev):
+    torch, dev = torch_dev
+    frames = np.stack([np.zeros((512, 512, 3), np.uint8), np.full((512, 512, 3), 128, np.uint8),
+                       np.full((512, 512, 3), 255, np.uint8)])
+    frames[2, 100:200, 300:400] = 0
+    hashes, quality = _gpu_hash(torch, dev, frames)
+    ref_h, ref_q = oracle.pdq_hash_frames(frames)
+    assert hashes.tobytes() == ref_h.tobytes() and (quality == ref_q).all()
+    assert hashes[0].tobytes() == bytes(32) and quality[0] == 0
+
+
+def test_video_hasher_streaming_matches_oracle():
+    """VideoHasher.hash_frame / finish (vpdqpy.py:113-119): > 3 staged batches so the pinned ring wraps,
+    quality filter >= 31 applied in finish()."""
+    frames = synth.synth_frames(110, seed=9)
+    frames[5] = 0  # a black frame: quality 0, must be dropped
+    frames[64] = 77  # flat frame
+    hasher = vpdq.VideoHasher(1, 512, 512, 0)
+    for k in range(0, 40):
+        hasher.hash_frame(frames[k].tobytes())
+    hasher.hash_frames(frames[40:])  # batch push, numpy buffer
+    phash, all_h, all_q = hasher.finish(return_all=True)
+    ref_h, ref_q = oracle.pdq_hash_frames(frames, nthreads=8)
+    assert all_h == ref_h.tobytes() and all_q == ref_q.tolist()
+    assert phash.bytes == ref_h[ref_q >= 31].tobytes() == oracle.video_hash(frames, nthreads=8)
+    assert len(phash) < 110
+    # the hasher is reusable after finish()
+    hasher.hash_frame(frames[0].tobytes())
+    assert hasher.finish().bytes == ref_h[0].tobytes()
+    assert len(hasher.finish()) == 0  # nothing pushed -> empty hash (legal, dedup.py:82)
+    with pytest.raises(ValueError):
+        hasher.hash_frame(b"\x00" * 100)
+    hasher.close()
+
+
+def test_host_batch_call_matches_oracle():
+    import ctypes as C
+
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    frames = synth.synth_frames(20, seed=13)
+    hashes = np.zeros((20, 32), np.uint8)
+    quality = np.zeros(20, np.int32)
+    _ffi.check(_ffi.lib().vpdq_b200_pdq_hash_frames_host(frames.ctypes.data_as(C.c_void_p), 3, 20, 512, 512,
+                                                         hashes.ctypes.data_as(C.c_void_p),
+                                                         quality.ctypes.data_as(C.c_void_p), 0))
+    ref_h, ref_q = oracle.pdq_hash_frames(frames, nthreads=8)
+    assert hashes.tobytes() == ref_h.tobytes() and (quality == ref_q).all()
+
+
+def test_large_batch_properties(torch_dev):
+    """Size-independent properties at a size the oracle cannot cover quickly: determinism, batch-split
+    invariance, and popcount 128 wherever the DCT values are distinct."""
+    torch, dev = torch_dev
+    from hydrus_video_deduplicator_b200 import device
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    frames = torch.randint(0, 256, (1024, 512, 512, 3), dtype=torch.uint8, device=dev, generator=g)
+    h1, q1 = device.hash_frames(frames)
+    h2, q2 = device.hash_frames(frames)
+    ha, qa = device.hash_frames(frames[:333])
+    hb, qb = device.hash_frames(frames[333:])
+    torch.cuda.synchronize()
+    assert torch.equal(h1, h2) and torch.equal(q1, q2)
+    assert torch.equal(h1, torch.cat([ha, hb])) and torch.equal(q1, torch.cat([qa, qb]))
+    pop = np.unpackbits(h1.cpu().numpy(), axis=1).sum(axis=1)
+    assert (pop == 128).all()
+    sample = frames[::97].cpu().numpy()
+    ref_h, ref_q = oracle.pdq_hash_frames(sample, nthreads=8)
+    assert h1[::97].cpu().numpy().tobytes() == ref_h.tobytes() and (q1[::97].cpu().numpy() == ref_q).all()
