@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -15,6 +16,7 @@
 namespace vpdq {
 
 static thread_local char t_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -142,6 +144,12 @@ extern "C" {
 const char* vpdq_b200_last_error(void) { return t_err; }
 int vpdq_b200_abi_version(void) { return 1; }
 
+int vpdq_b200_kernel_launches(uint64_t* count) {
+    if (!count) return VPDQ_B200_ERR_INVALID;
+    *count = g_launches.load();
+    return VPDQ_B200_OK;
+}
+
 int vpdq_b200_device_count(int* count) {
     if (!count) return VPDQ_B200_ERR_INVALID;
     *count = 0;
@@ -186,6 +194,52 @@ int vpdq_b200_pdq_hash_frames_dev(const uint8_t* d_frames, int channels, int64_t
                                     nullptr, d_scratch, scratch_bytes, stream);
 }
 
+// Per-device workspace of the one-shot host call, kept between calls (grow-only) so that a caller that
+// hashes batch after batch pays for cudaMalloc / stream creation once.
+namespace {
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t freed[2] = {nullptr, nullptr};
+    uint8_t* d_in[2] = {nullptr, nullptr};
+    void* d_scr[2] = {nullptr, nullptr};
+    uint8_t* d_hash[2] = {nullptr, nullptr};
+    int32_t* d_q[2] = {nullptr, nullptr};
+    size_t in_bytes = 0, scr_bytes = 0;
+    std::mutex mu;
+};
+constexpr int64_t kHostChunk = 256;  // frames per H2D/compute stage (201 MB of RGB24)
+HostPipe g_pipes[64];
+
+int host_pipe_prepare(HostPipe& p, size_t in_bytes, size_t scr_bytes) {
+    if (!p.ready) {
+        for (int b = 0; b < 2; ++b) {
+            VPDQ_CUDA(cudaStreamCreateWithFlags(&p.st[b], cudaStreamNonBlocking));
+            VPDQ_CUDA(cudaMalloc(&p.d_hash[b], kHostChunk * 32));
+            VPDQ_CUDA(cudaMalloc(&p.d_q[b], kHostChunk * sizeof(int32_t)));
+        }
+        p.ready = true;
+    }
+    if (in_bytes > p.in_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            if (p.d_in[b]) VPDQ_CUDA(cudaFree(p.d_in[b]));
+            p.d_in[b] = nullptr;
+            VPDQ_CUDA(cudaMalloc(&p.d_in[b], in_bytes));
+        }
+        p.in_bytes = in_bytes;
+    }
+    if (scr_bytes > p.scr_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            if (p.d_scr[b]) VPDQ_CUDA(cudaFree(p.d_scr[b]));
+            p.d_scr[b] = nullptr;
+            VPDQ_CUDA(cudaMalloc(&p.d_scr[b], scr_bytes));
+        }
+        p.scr_bytes = scr_bytes;
+    }
+    return VPDQ_B200_OK;
+}
+}  // namespace
+
 int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_t n_frames, int width, int height,
                                    uint8_t* h_hashes, int32_t* h_quality, int device) {
     int rc = check_frames(h_frames, channels, n_frames, width, height);
@@ -197,61 +251,40 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
     }
     DeviceGuard g(device);
     if (g.rc) return g.rc;
-
-    // two chunks in flight: the H2D copy of chunk c+1 overlaps the kernels of chunk c
-    const int64_t chunk = n_frames < 256 ? n_frames : 256;
-    const size_t fb = (size_t)kPlane * channels;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    uint8_t* d_in[2] = {nullptr, nullptr};
-    void* d_scr[2] = {nullptr, nullptr};
-    uint8_t* d_hash = nullptr;
-    int32_t* d_q = nullptr;
-    const size_t scr = pdq_scratch_bytes(chunk);
-    auto cleanup = [&]() {
-        for (int b = 0; b < 2; ++b) {
-            if (st[b]) cudaStreamSynchronize(st[b]);
-            if (d_in[b]) cudaFree(d_in[b]);
-            if (d_scr[b]) cudaFree(d_scr[b]);
-            if (st[b]) cudaStreamDestroy(st[b]);
-        }
-        if (d_hash) cudaFree(d_hash);
-        if (d_q) cudaFree(d_q);
-    };
-#define HOST_TRY(call)                                \
-    do {                                              \
-        cudaError_t e__ = (call);                     \
-        if (e__ != cudaSuccess) {                     \
-            cleanup();                                \
-            return ::vpdq::cuda_fail(e__, #call);     \
-        }                                             \
-    } while (0)
-    const int nbuf = n_frames > chunk ? 2 : 1;
-    for (int b = 0; b < nbuf; ++b) {
-        HOST_TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-        HOST_TRY(cudaMalloc(&d_in[b], (size_t)chunk * fb));
-        HOST_TRY(cudaMalloc(&d_scr[b], scr));
+    int dev = 0;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device index %d out of range", dev);
+        return VPDQ_B200_ERR_INVALID;
     }
-    HOST_TRY(cudaMalloc(&d_hash, (size_t)n_frames * 32));
-    HOST_TRY(cudaMalloc(&d_q, (size_t)n_frames * sizeof(int32_t)));
+    HostPipe& p = g_pipes[dev];
+    std::lock_guard<std::mutex> lk(p.mu);
+
+    // two stages in flight on two streams: the H2D copy of chunk c+1 overlaps the kernels of chunk c
+    const int64_t chunk = n_frames < kHostChunk ? n_frames : kHostChunk;
+    const size_t fb = (size_t)kPlane * channels;
+    const size_t scr = pdq_scratch_bytes(chunk);
+    rc = host_pipe_prepare(p, (size_t)chunk * fb, scr);
+    if (rc) return rc;
     int c = 0;
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, ++c) {
-        const int b = c % nbuf;
+        const int b = c & 1;
         const int64_t nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        HOST_TRY(cudaMemcpyAsync(d_in[b], h_frames + (size_t)f0 * fb, (size_t)nf * fb, cudaMemcpyHostToDevice, st[b]));
-        rc = pdq_launch(d_in[b], channels, nf, d_hash + (size_t)f0 * 32, d_q + f0, nullptr, nullptr, d_scr[b], scr,
-                        st[b]);
-        if (rc) {
-            cleanup();
-            return rc;
-        }
-        HOST_TRY(cudaMemcpyAsync(h_hashes + (size_t)f0 * 32, d_hash + (size_t)f0 * 32, (size_t)nf * 32,
-                                 cudaMemcpyDeviceToHost, st[b]));
-        HOST_TRY(cudaMemcpyAsync(h_quality + f0, d_q + f0, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st[b]));
+        VPDQ_CUDA(cudaMemcpyAsync(p.d_in[b], h_frames + (size_t)f0 * fb, (size_t)nf * fb, cudaMemcpyHostToDevice,
+                                  p.st[b]));
+        rc = pdq_launch(p.d_in[b], channels, nf, p.d_hash[b], p.d_q[b], nullptr, nullptr, p.d_scr[b], p.scr_bytes,
+                        p.st[b]);
+        if (rc) break;
+        VPDQ_CUDA(cudaMemcpyAsync(h_hashes + (size_t)f0 * 32, p.d_hash[b], (size_t)nf * 32, cudaMemcpyDeviceToHost,
+                                  p.st[b]));
+        VPDQ_CUDA(cudaMemcpyAsync(h_quality + f0, p.d_q[b], (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                  p.st[b]));
     }
-    for (int b = 0; b < nbuf; ++b) HOST_TRY(cudaStreamSynchronize(st[b]));
-#undef HOST_TRY
-    cleanup();
-    return VPDQ_B200_OK;
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaStreamSynchronize(p.st[b]);
+        if (e != cudaSuccess && rc == VPDQ_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
 }
 
 // ---- hasher handle -----------------------------------------------------------------------------------

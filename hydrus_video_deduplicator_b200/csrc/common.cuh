@@ -1,6 +1,8 @@
 // common.cuh -- shared declarations for libvpdq_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -17,6 +19,9 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// every kernel launch of this library bumps this (bench.py reports it as gpu_launches)
+extern std::atomic<uint64_t> g_launches;
 
 // Error plumbing shared by the host-side translation units.
 void set_error(const char* fmt, ...);

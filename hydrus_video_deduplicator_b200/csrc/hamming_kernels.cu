@@ -107,6 +107,7 @@ int hamming_scan_launch(const uint64_t* d_db, int64_t n_db, const int64_t* d_off
     const unsigned grid = (unsigned)(n_tiles < max_grid ? n_tiles : max_grid);
     k_hamming_scan<<<grid, kScanThreads, 0, stream>>>(d_db, n_db, d_offsets, n_videos, d_query, n_query, tol,
                                                       reinterpret_cast<unsigned long long*>(d_qmask), d_tcount);
+    g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;
 }
@@ -217,6 +218,7 @@ int hamming_pairs_launch(const uint64_t* d_q, int64_t n_q, const uint64_t* d_t, 
     dim3 grid((unsigned)q_tiles, (unsigned)t_splits);
     k_hamming_pairs<<<grid, kPairThreads, 0, stream>>>(d_q, n_q, d_t, n_t, t_chunk, tol, skip_diagonal, d_any,
                                                        reinterpret_cast<unsigned long long*>(d_pairs), cap, d_count);
+    g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;
 }

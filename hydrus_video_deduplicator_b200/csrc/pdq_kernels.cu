@@ -342,6 +342,7 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
         k4_colpass_finalize<<<(unsigned)nf, 256, 0, stream>>>(p3t, d_hashes + (size_t)f0 * 32, d_quality + f0,
                                                             d_a64 ? d_a64 + (size_t)f0 * 4096 : nullptr,
                                                             d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr);
+        g_launches += 4;
     }
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

@@ -54,6 +54,8 @@ typedef enum vpdq_b200_status {
 VPDQ_B200_API const char* vpdq_b200_last_error(void);
 VPDQ_B200_API int vpdq_b200_abi_version(void);
 VPDQ_B200_API int vpdq_b200_device_count(int* count);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+VPDQ_B200_API int vpdq_b200_kernel_launches(uint64_t* count);
 /* the 16 x 64 fp32 DCT table the kernels use (host copy; bit-identical to the oracle's) */
 VPDQ_B200_API int vpdq_b200_dct_matrix(float* out /* [16*64] */);
 
