@@ -1,0 +1,520 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the B200 VPDQ hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload hash|hamming]
+  (N > 1: launched by torchrun, one rank per GPU; rank 0 prints ONE JSON line)
+
+workload "hash" (default; BASELINE.json configs[1]: "hash 100k synthetic frames"):
+    a step = one pass of the PDQ frame-hash path over one batch of synthetic 512x512 RGB24 frames.
+    value = frames/s with the batch already resident in HBM (CUDA events on the launching stream, max over
+            ranks); e2e = the same through the host-pointer C ABI call (pinned host memory -> H2D -> kernels
+            -> D2H inside the timed region).  Each step's input (3.2 GB) is far larger than L2 (126 MB).
+    At N = 1 the JSON line also carries the Hamming figures (streaming scan GB/s vs the HBM peak at
+    n_query = 1/2/4/8, and 1M x 1M all-pairs comparisons/s) under "hamming".
+workload "hamming" (BASELINE.json configs[3]): pair-comparisons/s of the all-pairs kernel with the target
+    DB sharded over the ranks (1.25 M hashes per GPU, i.e. 10 M at 8 GPUs), queries replicated, and an
+    NCCL all_gather of the candidate bitmaps every step.
+
+--impl reference times the reference's CPU path (the golden-pinned oracle port; the real arithmetic lives
+in the absent hvdaccelerators wheel) on the host cores with all threads, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FRAME_BYTES = 512 * 512 * 3
+ALGO_BYTES_PER_FRAME = FRAME_BYTES + 32 + 4  # RGB24 in, hash + quality out
+HASH_BYTES = 32
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (recipe: /opt/skills/guides/B200_PROFILING.md)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        self.tmp.close()
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------------------
+def device_frames(torch, n: int, device, seed: int):
+    """[n, 512, 512, 3] u8 on the device: frame k is noise / smooth / blocks for k % 3 = 0 / 1 / 2
+    (the generator of tests/synth.py, restated with torch ops so that 100k frames take seconds)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device=device)
+    step = 256
+    for f0 in range(0, n, step):
+        m = min(step, n - f0)
+        blk = out[f0:f0 + m]
+        blk.copy_(torch.randint(0, 256, (m, 512, 512, 3), dtype=torch.uint8, device=device, generator=g))
+        ks = torch.arange(f0, f0 + m, device=device) % 3
+        i1 = torch.nonzero(ks == 1).flatten()
+        if i1.numel():
+            grid = torch.rand((i1.numel(), 3, 8, 8), device=device, generator=g) * 255.0
+            up = torch.nn.functional.interpolate(grid, size=(512, 512), mode="bilinear", align_corners=False)
+            blk[i1] = up.round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+        i2 = torch.nonzero(ks == 2).flatten()
+        if i2.numel():
+            small = torch.randint(0, 256, (i2.numel(), 32, 32, 3), dtype=torch.uint8, device=device, generator=g)
+            blk[i2] = small.repeat_interleave(16, dim=1).repeat_interleave(16, dim=2)
+    return out
+
+
+def device_hashes(torch, n: int, device, seed: int, planted_frac: float = 0.01):
+    """[n, 32] u8 random hashes with a planted_frac share of near-duplicates (20 flipped bits)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    h = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=device, generator=g)
+    k = int(n * planted_frac)
+    if k and n > 2 * k:
+        src = torch.randint(0, n // 2, (k,), device=device, generator=g)
+        dst = n // 2 + torch.randperm(n - n // 2, device=device, generator=g)[:k]
+        flip = torch.zeros((k, 32), dtype=torch.uint8, device=device)
+        flip[:, :5] = 0x0F
+        h[dst] = h[src] ^ flip
+    return h
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference (oracle port) -- the one place outside tests/ and smoke() that may run oracle/
+# ----------------------------------------------------------------------------------------------------
+def cpu_frames(n_frames: int):
+    import numpy as np
+
+    from tests import synth
+
+    base = synth.synth_frames(min(n_frames, 48), seed=0)
+    reps = (n_frames + len(base) - 1) // len(base)
+    return np.ascontiguousarray(np.concatenate([base] * reps)[:n_frames])
+
+
+def cpu_hash_rate(n_frames: int, threads: int, repeats: int = 1) -> tuple[float, float]:
+    """-> (frames/s, seconds) hashing n_frames synthetic frames `repeats` times on `threads` host threads"""
+    import oracle
+
+    frames = cpu_frames(n_frames)
+    oracle.pdq_hash_frames(frames[: min(len(frames), threads)], nthreads=threads)  # warm the tables
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        oracle.pdq_hash_frames(frames, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n_frames * repeats / dt, dt
+
+
+def cpu_pairs_rate(n: int, threads: int) -> tuple[float, float]:
+    import oracle
+    from tests import synth
+
+    h = synth.synth_hashes(n, seed=1)
+    t0 = time.perf_counter()
+    oracle.hamming_count_mt(h, h, 31, threads)
+    dt = time.perf_counter() - t0
+    return float(n) * n / dt, dt
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    cores = os.cpu_count() or 1
+    if args.workload == "hash":
+        import oracle
+
+        per_step = 16 * cores  # bounded sample: ~0.1-0.2 s of all-core work per step
+        frames = cpu_frames(per_step)
+        for _ in range(args.warmup):
+            oracle.pdq_hash_frames(frames, nthreads=cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle.pdq_hash_frames(frames, nthreads=cores)
+        secs = time.perf_counter() - t0
+        rate = per_step * args.steps / secs
+        value, unit, metric = rate, "frames/s", "frame_hashes_per_sec"
+        ms = secs / max(1, args.steps) * 1e3
+        sample = f"{args.steps} steps x {per_step} synthetic 512x512 RGB24 frames, {cores} threads (oracle port)"
+        config = hash_config(args, per_step)
+    else:
+        n = 16384
+        for _ in range(max(1, args.warmup) - 1):
+            cpu_pairs_rate(4096, cores)
+        rates = [cpu_pairs_rate(n, cores) for _ in range(max(1, min(args.steps, 5)))]
+        value = sum(r for r, _ in rates) / len(rates)
+        ms = sum(s for _, s in rates) / len(rates) * 1e3
+        unit, metric = "pair-comparisons/s", "pair_comparisons_per_sec"
+        sample = f"{len(rates)} x ({n} x {n}) 256-bit hashes, tolerance 31, {cores} threads (oracle port)"
+        config = hamming_config(args, 1)
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.workload == "hash" else "u64", "data": "synthetic", "config": config,
+        "impl": "reference",
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def hash_config(args, frames_per_step: int) -> dict:
+    return {"workload": "PDQ/VPDQ frame hash of synthetic 512x512 RGB24 frames (BASELINE configs[1]: 100k frames)",
+            "frames_per_step": frames_per_step, "frame_bytes": FRAME_BYTES,
+            "l2_policy": "each step's input batch is larger than L2 (126 MB); no flush needed",
+            "quality_filter": "none in the timed region (finish() filters on the host)"}
+
+
+def hamming_config(args, world: int) -> dict:
+    return {"workload": "all-pairs Hamming search, 256-bit hashes, tolerance 31 (BASELINE configs[2]/[3])",
+            "targets_per_gpu": args.shard_hashes, "queries_per_step": args.query_block,
+            "l2_policy": "L2 flushed between timed iterations by a 256 MB write (DB shard is L2-sized)"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import numpy as np
+    import torch
+
+    from hydrus_video_deduplicator_b200 import _ffi, device as dev_api, dist as hdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    rank, world, local = hdist.init()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _ffi.lib()
+    peak, peak_src = hbm_peak()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        hdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    extra = {}
+    if args.workload == "hash":
+        B = args.batch
+        pool_n = max(1, min(args.steps, args.pool_batches))
+        pool = [device_frames(torch, B, dev, seed=1000 * rank + p) for p in range(pool_n)]
+        for w in range(args.warmup):
+            dev_api.hash_frames(pool[w % pool_n])
+        sync_all()
+        sampler = ClockSampler(local)
+        launches0 = _ffi.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(args.steps):
+            hashes, quality = dev_api.hash_frames(pool[k % pool_n])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        hdist.barrier()
+        clocks = sampler.stop()
+        launches = _ffi.kernel_launches() - launches0
+        value = world * B * args.steps / (ms_total / 1e3)
+        ms_per_step = ms_total / args.steps
+        # roofline of the PDQ pipeline (the step's only kernels): algorithmic bytes / device time
+        achieved = B * ALGO_BYTES_PER_FRAME / (ms_per_step / 1e3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "kernel": "PDQ pipeline k1_luma_rowpass+k2_colpass+k3_rowpass_dec+k4_colpass_finalize",
+                    "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME}
+
+        # ---- end to end through the host-pointer C ABI (pinned host memory) ----
+        import ctypes as C
+
+        e2e_batch = min(B, args.e2e_batch)
+        h_frames = torch.empty((e2e_batch, 512, 512, 3), dtype=torch.uint8, pin_memory=True)
+        h_frames.copy_(pool[0][:e2e_batch])
+        h_hash = torch.empty((e2e_batch, 32), dtype=torch.uint8, pin_memory=True)
+        h_q = torch.empty((e2e_batch,), dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            _ffi.check(_ffi.lib().vpdq_b200_pdq_hash_frames_host(
+                C.c_void_p(h_frames.data_ptr()), 3, e2e_batch, 512, 512, C.c_void_p(h_hash.data_ptr()),
+                C.c_void_p(h_q.data_ptr()), local))
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * e2e_batch * e2e_steps / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": e2e_batch * FRAME_BYTES, "d2h_bytes_per_step": e2e_batch * 36,
+               "steps": e2e_steps, "frames_per_step": e2e_batch,
+               "api": "vpdq_b200_pdq_hash_frames_host (C ABI, pinned host buffers, 2 streams)"}
+        # the e2e results must equal the device-resident ones
+        chk_h, _ = dev_api.hash_frames(pool[0][:e2e_batch])
+        assert torch.equal(chk_h.cpu(), h_hash), "e2e hashes differ from the device-resident path"
+        metric, unit = "frame_hashes_per_sec", "frames/s"
+        config = hash_config(args, B)
+        config["parallelism"] = f"{world} x independent shards (no data-path collective)"
+        dtype = "f32"
+
+        if rank == 0 and world == 1 and not args.no_hamming:
+            extra["hamming"] = hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args)
+    else:
+        # ---- all-pairs Hamming, DB sharded over ranks, all_gather of candidate bitmaps ----
+        nt, nq = args.shard_hashes, args.query_block
+        shard = device_hashes(torch, nt, dev, seed=77 + rank)
+        queries = device_hashes(torch, nq, dev, seed=5)  # replicated (same seed on every rank)
+        count = torch.zeros((1,), dtype=torch.int64, device=dev)
+        pairs = torch.empty((1 << 20,), dtype=torch.int64, device=dev)
+        bitmap = torch.zeros(((nq + 31) // 32,), dtype=torch.int32, device=dev)
+
+        def step():
+            count.zero_()
+            bitmap.zero_()
+            _ffi.check(_ffi.lib().vpdq_b200_hamming_pairs_dev(
+                queries.data_ptr(), nq, shard.data_ptr(), nt, 31, 0, bitmap.data_ptr(), pairs.data_ptr(), 1 << 20,
+                count.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            return hdist.all_gather_bitmaps(bitmap)
+
+        for _ in range(args.warmup):
+            step()
+        sync_all()
+        sampler = ClockSampler(local)
+        launches0 = _ffi.kernel_launches()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush_l2()
+            ev[k][0].record()
+            gathered = step()
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+        hdist.barrier()
+        clocks = sampler.stop()
+        launches = _ffi.kernel_launches() - launches0
+        ms_per_step = ms_total / args.steps
+        value = float(world) * nt * nq / (ms_per_step / 1e3)
+        algo = (nt + nq) * HASH_BYTES
+        achieved = algo / (ms_per_step / 1e3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel": "k_hamming_pairs",
+                    "note": "all-pairs is POPC-issue bound, not HBM bound (compulsory bytes are tiny); see "
+                            "DESIGN.md -- the HBM-bound regime is the streaming scan reported by --workload hash"}
+        # e2e: host query block -> H2D -> kernel -> D2H of the bitmap
+        hq = queries.cpu().pin_memory()
+        hb = torch.empty_like(bitmap, device="cpu").pin_memory()
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            queries.copy_(hq, non_blocking=True)
+            g = step()
+            hb.copy_(hdist.or_reduce(g), non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": float(world) * nt * nq * e2e_steps / e2e_s, "unit": "pair-comparisons/s",
+               "h2d_bytes_per_step": nq * HASH_BYTES, "d2h_bytes_per_step": int(hb.numel() * 4), "steps": e2e_steps}
+        metric, unit = "pair_comparisons_per_sec", "pair-comparisons/s"
+        config = hamming_config(args, world)
+        config["parallelism"] = f"target DB sharded over {world} ranks, queries replicated, all_gather of bitmaps"
+        dtype = "u64"
+
+    if rank != 0:
+        return
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, pool[0] if args.workload == "hash" else None, torch)
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, pool0, torch) -> dict:
+    """The oracle port timed on this box's host cores (bounded sample), plus a parity spot-check."""
+    cores = os.cpu_count() or 1
+    if args.workload == "hash":
+        n = 24 * cores
+        rate_all, secs = cpu_hash_rate(n, cores, repeats=4)
+        rate_1, _ = cpu_hash_rate(24, 1)
+        import oracle
+        from hydrus_video_deduplicator_b200 import device as dev_api
+
+        sample = pool0[:9]
+        gh, gq = dev_api.hash_frames(sample)
+        rh, rq = oracle.pdq_hash_frames(sample.cpu().numpy(), nthreads=cores)
+        ok = bool((gh.cpu().numpy() == rh).all() and (gq.cpu().numpy() == rq).all())
+        return {"value": rate_all, "unit": "frames/s", "cores": cores, "kind": "port",
+                "sample": f"4 passes over {n} synthetic 512x512 RGB24 frames on {cores} threads ({secs:.1f} s); "
+                          f"1 thread: {rate_1:.1f} frames/s", "single_thread_value": rate_1,
+                "parity_spot_check": "9/9 frames bit-exact vs oracle" if ok else "MISMATCH vs oracle"}
+    rate, secs = cpu_pairs_rate(16384, cores)
+    return {"value": rate, "unit": "pair-comparisons/s", "cores": cores, "kind": "port",
+            "sample": f"16384 x 16384 hashes on {cores} threads ({secs:.1f} s)"}
+
+
+def hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args) -> dict:
+    """Streaming-scan GB/s (HBM-bound regime) and all-pairs comparisons/s on one GPU."""
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    out = {}
+    n_db = args.scan_hashes
+    db = device_hashes(torch, n_db, dev, seed=9)
+    fpv = 300
+    offsets = torch.arange(0, n_db + 1, fpv, dtype=torch.int64, device=dev)
+    if int(offsets[-1]) != n_db:
+        offsets = torch.cat([offsets, torch.tensor([n_db], dtype=torch.int64, device=dev)])
+    n_videos = offsets.numel() - 1
+    qmask = torch.zeros((n_videos,), dtype=torch.int64, device=dev)
+    scan = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    for nq in (1, 2, 4, 8, 16):
+        q = db[:nq].clone()
+
+        def run():
+            _ffi.check(_ffi.lib().vpdq_b200_hamming_scan_dev(db.data_ptr(), n_db, offsets.data_ptr(), n_videos,
+                                                             q.data_ptr(), nq, 31, qmask.data_ptr(), None, stream))
+
+        for _ in range(3):
+            run()
+        times = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run()
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        ms = statistics.mean(times)
+        gbs = n_db * HASH_BYTES / (ms / 1e3) / 1e9
+        scan[str(nq)] = {"ms": ms, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak,
+                         "pair_comparisons_per_s": n_db * nq / (ms / 1e3)}
+    out["scan"] = {"n_db": n_db, "db_bytes": n_db * HASH_BYTES, "frames_per_video": fpv, "by_n_query": scan,
+                   "peak_GB/s": peak, "peak_source": peak_src, "algorithmic_bytes_per_hash": HASH_BYTES,
+                   "note": "DB (320 MB) exceeds L2 (126 MB): every launch streams it from HBM"}
+    # all pairs, 1M x 1M
+    n = args.pairs_hashes
+    h = device_hashes(torch, n, dev, seed=10)
+    for _ in range(1):
+        dev_api.hamming_pairs(h[: n // 8], h, 31, skip_diagonal=True)
+    times, found = [], 0
+    for _ in range(2):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        found, _, _ = dev_api.hamming_pairs(h, h, 31, skip_diagonal=True)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = statistics.mean(times)
+    out["all_pairs"] = {"n_q": n, "n_t": n, "ms": ms, "pair_comparisons_per_s": float(n) * n / (ms / 1e3),
+                        "matches": int(found), "bound": "POPC issue (DB is L2 resident; compulsory HBM bytes = 64 MB)"}
+    return out
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=25)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=["hash", "hamming"], default="hash")
+    ap.add_argument("--batch", type=int, default=4096, help="frames per step per GPU (hash workload)")
+    ap.add_argument("--pool-batches", type=int, default=4, help="distinct device batches cycled through")
+    ap.add_argument("--e2e-batch", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--scan-hashes", type=int, default=10_000_000)
+    ap.add_argument("--pairs-hashes", type=int, default=1 << 20)
+    ap.add_argument("--shard-hashes", type=int, default=1_250_000)
+    ap.add_argument("--query-block", type=int, default=262_144)
+    ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

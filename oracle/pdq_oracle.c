@@ -226,22 +226,23 @@ static int hash_one(const uint8_t* px, int channels, int rows, int cols, uint8_t
                     float* a64_out, float* b16_out) {
     if (rows < 64 || cols < 64 || (channels != 1 && channels != 3)) return -1;
     const size_t npix = (size_t)rows * cols;
-    scratch_t s;
-    s.a = (float*)malloc(npix * sizeof(float));
-    s.b = (float*)malloc(npix * sizeof(float));
-    if (!s.a || !s.b) {
-        free(s.a);
-        free(s.b);
-        return -2;
+    /* per-thread scratch kept between frames (a fair baseline does not page-fault 2 MB per frame) */
+    static __thread float* tl_buf = NULL;
+    static __thread size_t tl_n = 0;
+    if (tl_n < 2 * npix) {
+        free(tl_buf);
+        tl_buf = (float*)malloc(2 * npix * sizeof(float));
+        tl_n = tl_buf ? 2 * npix : 0;
+        if (!tl_buf) return -2;
     }
+    scratch_t s;
+    s.a = tl_buf;
+    s.b = tl_buf + npix;
     if (channels == 3)
         luma_from_rgb(px, npix, s.a);
     else
         luma_from_gray(px, npix, s.a);
-    const int rc = hash_from_luma(&s, rows, cols, hash, quality, a64_out, b16_out);
-    free(s.a);
-    free(s.b);
-    return rc;
+    return hash_from_luma(&s, rows, cols, hash, quality, a64_out, b16_out);
 }
 
 /* replaces VideoHasher.hash_frame's per-frame work (vpdqpy.py:118); rgb = rows x cols x 3 */
