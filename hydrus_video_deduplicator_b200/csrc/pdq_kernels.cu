@@ -20,6 +20,8 @@
 // Passes 3/4 only produce the outputs the 64x64 decimation reads (rows/cols 8k+4) but still run the
 // full running sums, as exactness demands.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -312,37 +314,57 @@ size_t pdq_scratch_bytes(int64_t n_frames) {
     return (size_t)c * kScratchPerFrame;
 }
 
+// which pipeline hashes RGB frames: the fused kernel (default) or the v1 line kernels
+// (VPDQ_B200_PDQ_IMPL=lines; both are CUDA and bit-identical -- the switch exists for A/B measurements)
+static bool use_fused() {
+    static const bool fused = [] {
+        const char* e = getenv("VPDQ_B200_PDQ_IMPL");
+        return !(e && strcmp(e, "lines") == 0);
+    }();
+    return fused;
+}
+
 int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t* d_hashes, int32_t* d_quality,
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (n_frames == 0) return VPDQ_B200_OK;
-    int64_t chunk = (int64_t)(scratch_bytes / kScratchPerFrame);
+    const bool fused = channels == 3 && use_fused();
+    const size_t per_frame = fused ? fused_scratch_per_frame() : kScratchPerFrame;
+    int64_t chunk = (int64_t)(scratch_bytes / per_frame);
     if (chunk < 1) {
-        set_error("pdq: scratch too small (%zu bytes, need >= %zu)", scratch_bytes, kScratchPerFrame);
+        set_error("pdq: scratch too small (%zu bytes, need >= %zu)", scratch_bytes, per_frame);
         return VPDQ_B200_ERR_INVALID;
     }
-    if (chunk > kMaxChunk) chunk = kMaxChunk;
+    if (!fused && chunk > kMaxChunk) chunk = kMaxChunk;
     int rc = pdq_upload_tables();
     if (rc) return rc;
 
     const size_t frame_bytes = (size_t)kPlane * channels;
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const int64_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
-        float* p1t = static_cast<float*>(d_scratch);
-        float* p2 = p1t + (size_t)nf * kPlane;
-        float* p3t = p2 + (size_t)nf * kPlane;
-        const int64_t n_lines = nf * kDim;
-        const unsigned grid = (unsigned)((n_lines + 127) / 128);
         const uint8_t* src = d_frames + (size_t)f0 * frame_bytes;
-        if (channels == 3)
-            k1_luma_rowpass<3><<<grid, 128, 0, stream>>>(src, p1t, n_lines);
-        else
-            k1_luma_rowpass<1><<<grid, 128, 0, stream>>>(src, p1t, n_lines);
-        k2_colpass<<<grid, 128, 0, stream>>>(p1t, p2, n_lines);
-        k3_rowpass_dec<<<grid, 128, 0, stream>>>(p2, p3t, n_lines);
+        float* p3t;
+        if (fused) {
+            p3t = static_cast<float*>(d_scratch);
+            rc = fused_p123_launch(src, nf, p3t, stream);
+            if (rc) return rc;
+        } else {
+            float* p1t = static_cast<float*>(d_scratch);
+            float* p2 = p1t + (size_t)nf * kPlane;
+            p3t = p2 + (size_t)nf * kPlane;
+            const int64_t n_lines = nf * kDim;
+            const unsigned grid = (unsigned)((n_lines + 127) / 128);
+            if (channels == 3)
+                k1_luma_rowpass<3><<<grid, 128, 0, stream>>>(src, p1t, n_lines);
+            else
+                k1_luma_rowpass<1><<<grid, 128, 0, stream>>>(src, p1t, n_lines);
+            k2_colpass<<<grid, 128, 0, stream>>>(p1t, p2, n_lines);
+            k3_rowpass_dec<<<grid, 128, 0, stream>>>(p2, p3t, n_lines);
+            g_launches += 3;
+        }
         k4_colpass_finalize<<<(unsigned)nf, 256, 0, stream>>>(p3t, d_hashes + (size_t)f0 * 32, d_quality + f0,
                                                             d_a64 ? d_a64 + (size_t)f0 * 4096 : nullptr,
                                                             d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr);
-        g_launches += 4;
+        g_launches += 1;
     }
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;
