@@ -37,9 +37,9 @@ size_t pdq_scratch_bytes(int64_t n_frames);
 // chunk = number of frames whose intermediates are live at once (bounded by the scratch supplied)
 int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t* d_hashes, int32_t* d_quality,
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
-// fused luma + pass 1 + pass 2 + pass 3 (pdq_fused.cu): RGB24 frames -> p3t [n][64][512]
+// fused luma + Jarosz passes + decimation (pdq_fused.cu): RGB24 frames -> a64 [n][64][64]
 size_t fused_scratch_per_frame();
-int fused_p123_launch(const uint8_t* d_frames, int64_t n_frames, float* d_p3t, cudaStream_t stream);
+int fused_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int pdq_upload_tables();  // DCT matrix -> device (once per device)
 const float* pdq_host_dct();
 

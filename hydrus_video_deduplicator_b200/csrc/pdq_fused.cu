@@ -1,18 +1,20 @@
-// pdq_fused.cu -- kx_fused_p123: luma + row pass 1 + column pass 1 + row pass 2 of the PDQ Jarosz filter
-// in ONE persistent kernel, fp32 intermediates never leaving the SM (sm_100a).
+// pdq_fused.cu -- kx_fused_jarosz: luma + the four Jarosz box-filter passes + 64x64 decimation of the PDQ
+// hash in ONE persistent kernel, fp32 intermediates never leaving the SM (sm_100a).
 //
-// Replaces k1/k2/k3 of pdq_kernels.cu (same arithmetic, same order, bit-identical results): HBM traffic per
-// frame drops from ~5.2 MB (v1: P1 and P2 planes round-trip through L2/HBM) to the algorithmic 786 KB in +
-// 128 KB of decimated row-pass-2 output that k4_colpass_finalize consumes.
+// Replaces k1/k2/k3 and the column-pass half of k4 of pdq_kernels.cu (same arithmetic, same order,
+// bit-identical results).  HBM traffic per frame drops from ~5.2 MB (v1: the P1/P2 planes round-trip
+// through L2/HBM) to the algorithmic 786 KB in + 16 KB out (the decimated plane k5_finalize consumes).
 //
 // Structure (details and the index algebra: pdq_fused_core.h, which the CPU emulator also compiles):
 //   * persistent grid, one CTA of 16 warps per SM, each CTA owns a contiguous range of frames;
 //   * RGB rows are staged by TMA (cp.async.bulk.tensor.2d, one 32-row x 112-byte box per warp per step,
-//     2-deep ring with per-warp mbarriers; SASS: UTMALDG) -- out-of-bounds box parts come back as zeros,
-//     which is exactly what the two drain steps of every running sum need;
-//   * a 32x32 fp32 tile per warp in shared memory (XOR-swizzled, conflict free for lane=row float4 and
-//     lane=column scalar access) is the hand-over between the row roles and the column role; two CTA
-//     barriers per step separate them (bulk-synchronous wavefront, no other inter-warp signalling).
+//     per-warp mbarrier; SASS: UTMALDG).  The staged row is pulled into registers at the top of the step
+//     and the next box is requested at once, so one stage per warp suffices.  Out-of-bounds box parts
+//     come back as zeros, which is exactly what the two drain steps of every running sum need;
+//   * 32x32 fp32 tiles in shared memory (XOR-swizzled: conflict free for lane=row float4 and lane=column
+//     scalar access), double buffered by step parity, are the hand-over between row and column roles;
+//   * every warp runs its four roles (P1..P4) in the same step, interleaved, and ONE CTA barrier per step
+//     keeps the wavefront (bulk-synchronous; no other inter-warp signalling).
 #include <cuda.h>
 
 #include <mutex>
@@ -26,9 +28,10 @@ using namespace vpdq_core;
 constexpr int kFusedThreads = 512;
 
 struct FusedSmem {
-    alignas(128) uint8_t raw[2][kBands][kRawBoxBytes];  // 114 688 B  TMA destinations
-    alignas(16) float slot[kBands][kTile * kTile];      //  65 536 B  tile hand-over
-    alignas(8) unsigned long long bar[2][kBands];       //     256 B  mbarriers
+    alignas(128) uint8_t raw[kBands][kRawBoxBytes];   //  57 344 B  TMA destinations (one stage per warp)
+    alignas(16) float slot[2][kBands][kTile * kTile];  // 131 072 B  tile hand-over, by step parity
+    alignas(16) float t3[2][kBands * kT3Strip];        //  18 432 B  P3 -> P4 hand-over, by step parity
+    alignas(8) unsigned long long bar[kBands];         //     128 B  mbarriers
 };
 
 __device__ int g_fused_timeout = 0;  // set if an mbarrier wait gave up (never expected)
@@ -67,8 +70,8 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
-    kx_fused_p123(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames,
-                  long long n_frames_total, float* __restrict__ p3t) {
+    kx_fused_jarosz(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames,
+                    long long n_frames_total, float* __restrict__ a64) {
     extern __shared__ __align__(128) uint8_t smem_bytes[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_bytes);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,78 +82,61 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
     if (F == 0) return;
     const long long total_rows = n_frames_total * 512;
 
-    if (lane == 0) {
-        mbar_init(&sm.bar[0][w], 1);
-        mbar_init(&sm.bar[1][w], 1);
-    }
+    if (lane == 0) mbar_init(&sm.bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    const int u_first = (w == 15) ? -16 : 0;
+    const int u_first = p1_first(w);
     auto issue = [&](int u) {  // lane 0: stage the raw RGB box of P1 tile u of this warp's band
-        const int st = (u - u_first) & 1;
-        mbar_expect_tx(&sm.bar[st][w], kRawBoxBytes);
-        tma_load_2d(&sm.raw[st][w][0], &tmap, p1_box_x(u & 15), (int)p1_row0(f_begin, floor_div16(u), w),
-                    &sm.bar[st][w]);
+        mbar_expect_tx(&sm.bar[w], kRawBoxBytes);
+        tma_load_2d(&sm.raw[w][0], &tmap, p1_box_x(u & 15), (int)p1_row0(f_begin, floor_div16(u), w), &sm.bar[w]);
     };
-    if (lane == 0) {
-        if (p1_live(u_first, w, F)) issue(u_first);
-        if (p1_live(u_first + 1, w, F)) issue(u_first + 1);
-    }
+    if (lane == 0 && p1_live(u_first, w, F)) issue(u_first);
 
-    Chain c1, c2, c3;
-    c1.init();
-    c2.init();
-    c3.init();
-    float p0 = 0.0f, p1 = 0.0f;
+    LaneState st;
+    st.init();
 
     const int steps = num_steps(F);
     for (int T = 0; T < steps; ++T) {
-        // ---------------- phase A: row roles (lane = row) ----------------
-        {
-            const int u = sched_u3(T, w);
-            if (p3_live(u, F)) {
-                float* out = p3t + (size_t)(f_begin + (u >> 4)) * (64 * 512) + 32 * w + lane;
-                p3_lane(c3, sm.slot[w], lane, u & 15, out);
-            }
-        }
-        {
-            const int u = sched_u12(T, w);
-            if (p1_live(u, w, F)) {
-                const int strip = u & 15;
-                const int k = u - u_first;
-                uint32_t first2[2] = {0u, 0u};
-                if (strip == 0) {
-                    const long long R = p1_row0(f_begin, floor_div16(u), w) + lane;
-                    if (R >= 0 && R < total_rows) {
-                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(frames + (size_t)R * 1536));
-                        first2[0] = v.x;
-                        first2[1] = v.y;
-                    }
+        const int u1 = sched_u(T, 1, w), u2 = sched_u(T, 2, w), u3 = sched_u(T, 3, w), u4 = sched_u(T, 4, w);
+        StepArgs a;
+        a.live1 = p1_live(u1, w, F);
+        a.live2 = p2_live(u2, F);
+        a.live3 = p34_live(u3, F);
+        a.live4 = p34_live(u4, F);
+        a.s1 = u1 & 15; a.b2 = u2 & 15; a.s3 = u3 & 15; a.b4 = u4 & 15;
+        a.tile_a = sm.slot[T & 1][w];
+        a.tile_b = sm.slot[(T - 1) & 1][a.b2];
+        a.t3_w = sm.t3[T & 1] + a.s3 * kT3Strip;
+        a.t3_r = sm.t3[(T - 1) & 1] + w * kT3Strip;
+        a.a_out = a64 + (size_t)(a.live4 ? (f_begin + (u4 >> 4)) : f_begin) * 4096 + 4 * w + (lane & 3);
+
+        uint32_t first2[2] = {0u, 0u};
+        uint32_t raw[kRawWords];
+        if (a.live1) {
+            if (a.s1 == 0) {
+                const long long R = p1_row0(f_begin, floor_div16(u1), w) + lane;
+                if (R >= 0 && R < total_rows) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(frames + (size_t)R * 1536));
+                    first2[0] = v.x;
+                    first2[1] = v.y;
                 }
-                mbar_wait(&sm.bar[k & 1][w], (uint32_t)((k >> 1) & 1));
-                const uint4* rr = reinterpret_cast<const uint4*>(&sm.raw[k & 1][w][lane * kRawPitch]);
-                uint32_t raw[kRawWords];
+            }
+            mbar_wait(&sm.bar[w], (uint32_t)((u1 - u_first) & 1));
+            const uint4* rr = reinterpret_cast<const uint4*>(&sm.raw[w][lane * kRawPitch]);
 #pragma unroll
-                for (int q = 0; q < kRawWords / 4; ++q) {
-                    const uint4 v = rr[q];
-                    raw[4 * q + 0] = v.x; raw[4 * q + 1] = v.y; raw[4 * q + 2] = v.z; raw[4 * q + 3] = v.w;
-                }
-                p1_lane(c1, raw, first2, sm.slot[w], lane, strip);
-                __syncwarp();  // every lane has read its staged row: the stage may be refilled
-                if (lane == 0 && p1_live(u + 2, w, F)) issue(u + 2);
+            for (int q = 0; q < kRawWords / 4; ++q) {
+                const uint4 v = rr[q];
+                raw[4 * q + 0] = v.x; raw[4 * q + 1] = v.y; raw[4 * q + 2] = v.z; raw[4 * q + 3] = v.w;
             }
+            __syncwarp();  // every lane holds its staged row in registers: the stage may be refilled now
+            if (lane == 0 && p1_live(u1 + 1, w, F)) issue(u1 + 1);
+        } else {
+#pragma unroll
+            for (int q = 0; q < kRawWords; ++q) raw[q] = 0u;
         }
-        __syncthreads();
-        // ---------------- phase B: column role (lane = column), in place ----------------
-        {
-            const int u = sched_u12(T, w);
-            if (p2_live(u, F)) {
-                const int band = u & 15;
-                p2_lane(c2, p0, p1, sm.slot[band], lane, band, u < 0);
-            }
-        }
+        fused_step(st, a, raw, first2, lane);
         __syncthreads();
     }
 }
@@ -175,10 +161,10 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-size_t fused_scratch_per_frame() { return (size_t)64 * 512 * sizeof(float); }
+size_t fused_scratch_per_frame() { return (size_t)64 * 64 * sizeof(float); }
 
-// RGB24 frames -> p3t [n][64][512] (row pass 2 at the 64 decimated columns, transposed)
-int fused_p123_launch(const uint8_t* d_frames, int64_t n_frames, float* d_p3t, cudaStream_t stream) {
+// RGB24 frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane
+int fused_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream) {
     EncodeTiledFn encode = get_encode();
     if (!encode) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -204,13 +190,13 @@ int fused_p123_launch(const uint8_t* d_frames, int64_t n_frames, float* d_p3t, c
     {
         std::lock_guard<std::mutex> lk(mu);
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_p123, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_jarosz, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(FusedSmem)));
             if (dev >= 0 && dev < 64) attr_done[dev] = true;
         }
     }
     const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);  // persistent: one CTA per SM
-    kx_fused_p123<<<grid, kFusedThreads, sizeof(FusedSmem), stream>>>(tmap, d_frames, (long long)n_frames, d_p3t);
+    kx_fused_jarosz<<<grid, kFusedThreads, sizeof(FusedSmem), stream>>>(tmap, d_frames, (long long)n_frames, d_a64);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

@@ -179,17 +179,29 @@ __global__ void __launch_bounds__(128) k3_rowpass_dec(const float* __restrict__ 
     box_line_dec(p2 + (size_t)line * kDim, [&](int m, float y) { dst[(size_t)m * kDim] = y; });
 }
 
+// x / 255.0f, correctly rounded, branch free: q = RN(x*c), r = x - 255q (exact, FMA), q' = RN(q + r*c) with
+// c = RN(1/255).  Equal to IEEE x / 255.0f for EVERY finite float (tests/emu/div3_check.c 255).
+__device__ __forceinline__ float div255(float x) {
+    const float c = 0.00392156886f;  // 0x3B808081
+    const float q = fmul(x, c);
+    const float r = __fmaf_rn(-255.0f, q, x);
+    return __fmaf_rn(r, c, q);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K4: one CTA (256 threads) per frame.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kDP = 65;  // padded pitch of the 16x64 tables in shared memory
 
-__global__ void __launch_bounds__(256) k4_colpass_finalize(const float* __restrict__ p3t,
+// FROM_A = false: `in` is p3t [n][64][512] (v1 line kernels): run column pass 2 here.
+// FROM_A = true : `in` is a64 [n][64][64] (fused kernel already did column pass 2 + decimation).
+template <bool FROM_A>
+__global__ void __launch_bounds__(256) k4_colpass_finalize(const float* __restrict__ in,
                                                            uint8_t* __restrict__ hashes,
                                                            int32_t* __restrict__ quality,
                                                            float* __restrict__ a64_dbg,
                                                            float* __restrict__ b16_dbg) {
-    __shared__ float A[kDec][kDec];   // decimated 64x64 plane
+    __shared__ __align__(16) float A[kDec][kDec];   // decimated 64x64 plane
     __shared__ float D[16][kDP];      // DCT rows
     __shared__ float T[16][kDP];      // D * A
     __shared__ __align__(16) float B[256];
@@ -202,9 +214,14 @@ __global__ void __launch_bounds__(256) k4_colpass_finalize(const float* __restri
     for (int e = t; e < 16 * 64; e += 256) D[e >> 6][e & 63] = c_dct[e];
     if (t == 0) g_sum = 0;
 
-    // column pass 2 on the 64 surviving columns; outputs at rows 8m+4 are the decimated plane
-    if (t < kDec) {
-        const float* line = p3t + (size_t)f * (kDec * kDim) + (size_t)t * kDim;
+    if (FROM_A) {
+        const float4* src = reinterpret_cast<const float4*>(in + (size_t)f * (kDec * kDec));
+        float4* dst = reinterpret_cast<float4*>(&A[0][0]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[t + 256 * e] = __ldg(src + t + 256 * e);
+    } else if (t < kDec) {
+        // column pass 2 on the 64 surviving columns; outputs at rows 8m+4 are the decimated plane
+        const float* line = in + (size_t)f * (kDec * kDim) + (size_t)t * kDim;
         box_line_dec(line, [&](int m, float y) { A[m][t] = y; });
     }
     __syncthreads();
@@ -218,8 +235,8 @@ __global__ void __launch_bounds__(256) k4_colpass_finalize(const float* __restri
         for (int e = t; e < kDec * kDec; e += 256) {
             const int i = e >> 6, j = e & 63;
             const float u = A[i][j];
-            if (i < 63) g += abs(__float2int_rz(fdiv(fmul(fsub(u, A[i + 1][j]), 100.0f), 255.0f)));
-            if (j < 63) g += abs(__float2int_rz(fdiv(fmul(fsub(u, A[i][j + 1]), 100.0f), 255.0f)));
+            if (i < 63) g += abs(__float2int_rz(div255(fmul(fsub(u, A[i + 1][j]), 100.0f))));
+            if (j < 63) g += abs(__float2int_rz(div255(fmul(fsub(u, A[i][j + 1]), 100.0f))));
         }
         g = __reduce_add_sync(0xffffffffu, g);
         if ((t & 31) == 0) atomicAdd(&g_sum, g);
@@ -342,15 +359,19 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const int64_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         const uint8_t* src = d_frames + (size_t)f0 * frame_bytes;
-        float* p3t;
+        uint8_t* hp = d_hashes + (size_t)f0 * 32;
+        int32_t* qp = d_quality + f0;
+        float* adbg = d_a64 ? d_a64 + (size_t)f0 * 4096 : nullptr;
+        float* bdbg = d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr;
         if (fused) {
-            p3t = static_cast<float*>(d_scratch);
-            rc = fused_p123_launch(src, nf, p3t, stream);
+            float* a64 = static_cast<float*>(d_scratch);
+            rc = fused_jarosz_launch(src, nf, a64, stream);
             if (rc) return rc;
+            k4_colpass_finalize<true><<<(unsigned)nf, 256, 0, stream>>>(a64, hp, qp, adbg, bdbg);
         } else {
             float* p1t = static_cast<float*>(d_scratch);
             float* p2 = p1t + (size_t)nf * kPlane;
-            p3t = p2 + (size_t)nf * kPlane;
+            float* p3t = p2 + (size_t)nf * kPlane;
             const int64_t n_lines = nf * kDim;
             const unsigned grid = (unsigned)((n_lines + 127) / 128);
             if (channels == 3)
@@ -360,10 +381,8 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
             k2_colpass<<<grid, 128, 0, stream>>>(p1t, p2, n_lines);
             k3_rowpass_dec<<<grid, 128, 0, stream>>>(p2, p3t, n_lines);
             g_launches += 3;
+            k4_colpass_finalize<false><<<(unsigned)nf, 256, 0, stream>>>(p3t, hp, qp, adbg, bdbg);
         }
-        k4_colpass_finalize<<<(unsigned)nf, 256, 0, stream>>>(p3t, d_hashes + (size_t)f0 * 32, d_quality + f0,
-                                                            d_a64 ? d_a64 + (size_t)f0 * 4096 : nullptr,
-                                                            d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr);
         g_launches += 1;
     }
     VPDQ_CUDA(cudaGetLastError());
