@@ -63,7 +63,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -286,7 +286,6 @@ def run_b200(args) -> None:
         torch.cuda.synchronize()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         hdist.barrier()
-        clocks = sampler.stop()
         launches = _ffi.kernel_launches() - launches0
         value = world * B * args.steps / (ms_total / 1e3)
         ms_per_step = ms_total / args.steps
@@ -321,6 +320,7 @@ def run_b200(args) -> None:
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        clocks = sampler.stop()  # sampled across both timed regions (device-resident steps, then e2e steps)
         e2e = {"value": world * e2e_batch * e2e_steps / e2e_s, "unit": "frames/s",
                "h2d_bytes_per_step": e2e_batch * FRAME_BYTES, "d2h_bytes_per_step": e2e_batch * 36,
                "steps": e2e_steps, "frames_per_step": e2e_batch,
@@ -395,6 +395,9 @@ def run_b200(args) -> None:
         config["parallelism"] = f"target DB sharded over {world} ranks, queries replicated, all_gather of bitmaps"
         dtype = "u64"
 
+    if world > 1:
+        hdist.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     line = {

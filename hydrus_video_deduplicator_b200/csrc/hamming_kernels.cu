@@ -9,8 +9,9 @@
 //
 //   k_hamming_scan   streaming regime (the reference's real call pattern: one query video against the
 //                    whole DB).  One thread per DB hash, one 256-bit load (LDG.E.256) per hash, the
-//                    <= 64 query hashes broadcast from shared memory.  HBM-bound for small n_query:
-//                    algorithmic traffic = 32 B per DB hash.
+//                    <= 64 query hashes broadcast from shared memory, 96-bit carry-save prefilter
+//                    (2 POPC per pair).  HBM-bound up to ~10 resident queries: algorithmic traffic =
+//                    32 B per DB hash.
 //   k_hamming_pairs  all-pairs regime (1M x 1M).  The DB is L2-resident there and the kernel is bound
 //                    by POPC issue (XU pipe, measured 16 POPC/clk/SM), so the inner loop is a 96-bit
 //                    prefilter with a carry-save step: for the three xor words x0,x1,x2,
@@ -48,6 +49,19 @@ __device__ __forceinline__ int64_t video_of(const int64_t* __restrict__ offsets,
     return lo;
 }
 
+// distance over the first 96 bits with 2 POPC (carry-save adder over the three xor words).  The two 3-input
+// functions are pinned to one LOP3 each (xor3 = 0x96, majority = 0xE8) and the final  ps + 2*pc  goes to the
+// otherwise idle FMA pipe (IMAD), so the ALU pipe carries 5 ops per pair and the XU pipe 2.
+__device__ __forceinline__ int prefix96_distance(const uint32_t (&q)[3], const uint4& t) {
+    const uint32_t x0 = q[0] ^ t.x, x1 = q[1] ^ t.y, x2 = q[2] ^ t.z;
+    uint32_t sum, carry, d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(x0), "r"(x1), "r"(x2));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(x0), "r"(x1), "r"(x2));
+    const uint32_t ps = __popc(sum), pc = __popc(carry);
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d) : "r"(pc), "r"(ps));
+    return (int)d;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // streaming scan
 // ---------------------------------------------------------------------------------------------------
@@ -78,15 +92,27 @@ __global__ void __launch_bounds__(kScanThreads)
             const int64_t idx = base + (int64_t)u * kScanThreads;
             if (idx >= n_db) continue;
             unsigned long long mask = 0ull;
-            for (int qi = 0; qi < n_query; ++qi) {
+            const uint32_t h3[3] = {h[u][0], h[u][1], h[u][2]};
+            auto exact = [&](int qi, int d96) {  // rare: the 96-bit prefix is within tol
                 const uint4 a = q_s[2 * qi], b = q_s[2 * qi + 1];
-                int d = __popc(h[u][0] ^ a.x) + __popc(h[u][1] ^ a.y) + __popc(h[u][2] ^ a.z) +
-                        __popc(h[u][3] ^ a.w);
-                if (d <= tol) {
-                    d += __popc(h[u][4] ^ b.x) + __popc(h[u][5] ^ b.y) + __popc(h[u][6] ^ b.z) +
-                         __popc(h[u][7] ^ b.w);
-                    if (d <= tol) mask |= 1ull << qi;
+                const int d = d96 + __popc(h[u][3] ^ a.w) + __popc(h[u][4] ^ b.x) + __popc(h[u][5] ^ b.y) +
+                              __popc(h[u][6] ^ b.z) + __popc(h[u][7] ^ b.w);
+                if (d <= tol) mask |= 1ull << qi;
+            };
+            int qi = 0;
+            for (; qi + 4 <= n_query; qi += 4) {  // four independent prefilters in flight (ILP)
+                int d[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = prefix96_distance(h3, q_s[2 * (qi + j)]);  // 2 POPC each
+                if (min(min(d[0], d[1]), min(d[2], d[3])) <= tol) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (d[j] <= tol) exact(qi + j, d[j]);
                 }
+            }
+            for (; qi < n_query; ++qi) {
+                const int d = prefix96_distance(h3, q_s[2 * qi]);
+                if (d <= tol) exact(qi, d);
             }
             if (mask) {
                 const int64_t v = offsets ? video_of(offsets, n_videos, idx) : idx;
@@ -122,14 +148,6 @@ constexpr int kPairThreads = 256;
 constexpr int kPairQR = 8;                            // queries per thread (96-bit prefixes in registers)
 constexpr int kPairQTile = kPairThreads * kPairQR;    // 2048 queries per CTA
 constexpr int kPairTTile = 1024;                      // target prefixes per shared-memory stage (16 KB)
-
-// distance over the first 96 bits with 2 POPC (carry-save adder over the three xor words)
-__device__ __forceinline__ int prefix96_distance(const uint32_t (&q)[3], const uint4& t) {
-    const uint32_t x0 = q[0] ^ t.x, x1 = q[1] ^ t.y, x2 = q[2] ^ t.z;
-    const uint32_t sum = x0 ^ x1 ^ x2;
-    const uint32_t carry = (x0 & x1) | (x2 & (x0 | x1));
-    return __popc(sum) + 2 * __popc(carry);
-}
 
 __device__ __forceinline__ int full_distance(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b) {
     return __popcll(__ldg(a) ^ __ldg(b)) + __popcll(__ldg(a + 1) ^ __ldg(b + 1)) +

@@ -161,3 +161,43 @@ def test_large_scale_properties(torch_dev):
     assert n1 == n2 and a == b
     for k in range(0, 1000, 37):
         assert (3 * k, 3 * k + 1) in a and (3 * k + 1, 3 * k) in a
+
+
+def test_baseline_sizes_vs_oracle_slabs(torch_dev):
+    """BASELINE configs[2]/[3] sizes: a 10M-hash streaming scan and a 1M-target all-pairs slab, each checked
+    against the oracle on as many rows as the CPU finishes in seconds."""
+    torch, dev = torch_dev
+    from hydrus_video_deduplicator_b200 import device
+
+    g = torch.Generator(device=dev).manual_seed(11)
+    n = 10_000_000
+    db = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    q = db[torch.randint(0, n, (64,), device=dev, generator=g)].clone()
+    flips = torch.zeros((64, 32), dtype=torch.uint8, device=dev)
+    flips[::2, :4] = 0xFF      # every other query sits at distance 32 from its source: just outside
+    flips[1::2, :3] = 0xFF     # the rest at 24 ... 
+    flips[1::2, 3] = 0x7F      # ... + 7 = 31: just inside
+    q ^= flips
+    off = torch.arange(0, n + 1, 300, dtype=torch.int64, device=dev)
+    if int(off[-1]) != n:
+        off = torch.cat([off, torch.tensor([n], dtype=torch.int64, device=dev)])
+    qmask = device.hamming_scan(db, q, off, 31).cpu().numpy()
+    db_h, q_h, off_h = db.cpu().numpy(), q.cpu().numpy(), off.cpu().numpy()
+    ref = oracle.hamming_pairs(q_h, db_h, 31)
+    want = np.zeros(len(off_h) - 1, np.uint64)
+    for i, j in ref:
+        want[np.searchsorted(off_h, j, side="right") - 1] |= np.uint64(1) << np.uint64(i)
+    assert (qmask.view(np.uint64) == want).all()
+    assert len(ref) == 32  # exactly the distance-31 half matches (random 256-bit words never come close)
+
+    m = 1 << 20
+    slab = db[:m]
+    nq = 2048
+    cnt, pairs, _ = device.hamming_pairs(q, slab, 31)
+    assert cnt == len(oracle.hamming_pairs(q_h, db_h[:m], 31))
+    planted = slab[:nq].clone()
+    planted[:, 31] ^= 0x55  # distance 4 from rows 0..nq-1
+    cnt, pairs, bitmap = device.hamming_pairs(planted, slab, 31)
+    refp = oracle.hamming_pairs(planted.cpu().numpy(), db_h[:m], 31)
+    assert cnt == len(refp) == nq
+    assert {tuple(p) for p in pairs.cpu().numpy().tolist()} == {tuple(p) for p in refp.tolist()}

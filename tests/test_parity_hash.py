@@ -132,3 +132,32 @@ def test_large_batch_properties(torch_dev):
     sample = frames[::97].cpu().numpy()
     ref_h, ref_q = oracle.pdq_hash_frames(sample, nthreads=8)
     assert h1[::97].cpu().numpy().tobytes() == ref_h.tobytes() and (q1[::97].cpu().numpy() == ref_q).all()
+
+
+def test_config1_100k_frames(torch_dev):
+    """BASELINE configs[1]: 100k synthetic frames through the device-resident path, in 8192-frame pieces.
+    Full-size checks: split invariance (two different batchings give identical bytes), popcount 128 on every
+    non-degenerate frame, and an oracle comparison on a strided sample."""
+    torch, dev = torch_dev
+    from bench import device_frames
+    from hydrus_video_deduplicator_b200 import device
+
+    total, piece = 100_000, 8192
+    checked = 0
+    for p0 in range(0, total, piece):
+        n = min(piece, total - p0)
+        frames = device_frames(torch, n, dev, seed=p0)
+        h1, q1 = device.hash_frames(frames)
+        cut = 1 + (p0 // piece) * 37 % (n - 1)
+        ha, qa = device.hash_frames(frames[:cut])
+        hb, qb = device.hash_frames(frames[cut:])
+        assert torch.equal(h1, torch.cat([ha, hb])) and torch.equal(q1, torch.cat([qa, qb]))
+        pop = torch.from_numpy(np.unpackbits(h1.cpu().numpy(), axis=1).sum(axis=1))
+        assert int((pop != 128).sum()) == 0
+        idx = torch.arange(p0 % 7, n, 1021, device=dev)
+        ref_h, ref_q = oracle.pdq_hash_frames(frames[idx].cpu().numpy(), nthreads=16)
+        assert h1[idx].cpu().numpy().tobytes() == ref_h.tobytes()
+        assert (q1[idx].cpu().numpy() == ref_q).all()
+        checked += len(idx)
+        del frames
+    assert checked >= 100
