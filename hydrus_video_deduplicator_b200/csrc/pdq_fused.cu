@@ -113,30 +113,35 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
         a.a_out = a64 + (size_t)(a.live4 ? (f_begin + (u4 >> 4)) : f_begin) * 4096 + 4 * w + (lane & 3);
 
         uint32_t first2[2] = {0u, 0u};
-        uint32_t raw[kRawWords];
-        if (a.live1) {
-            if (a.s1 == 0) {
-                const long long R = p1_row0(f_begin, floor_div16(u1), w) + lane;
-                if (R >= 0 && R < total_rows) {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(frames + (size_t)R * 1536));
-                    first2[0] = v.x;
-                    first2[1] = v.y;
-                }
+        if (a.live1 && a.s1 == 0) {
+            const long long R = p1_row0(f_begin, floor_div16(u1), w) + lane;
+            if (R >= 0 && R < total_rows) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(frames + (size_t)R * 1536));
+                first2[0] = v.x;
+                first2[1] = v.y;
             }
-            mbar_wait(&sm.bar[w], (uint32_t)((u1 - u_first) & 1));
+        }
+        if (a.live1) mbar_wait(&sm.bar[w], (uint32_t)((u1 - u_first) & 1));
+        // (when P1 is not live the staged bytes are stale; its results are never stored)
+        uint32_t raw[kRawWords];
+        {
             const uint4* rr = reinterpret_cast<const uint4*>(&sm.raw[w][lane * kRawPitch]);
 #pragma unroll
             for (int q = 0; q < kRawWords / 4; ++q) {
                 const uint4 v = rr[q];
                 raw[4 * q + 0] = v.x; raw[4 * q + 1] = v.y; raw[4 * q + 2] = v.z; raw[4 * q + 3] = v.w;
             }
-            __syncwarp();  // every lane holds its staged row in registers: the stage may be refilled now
-            if (lane == 0 && p1_live(u1 + 1, w, F)) issue(u1 + 1);
-        } else {
-#pragma unroll
-            for (int q = 0; q < kRawWords; ++q) raw[q] = 0u;
         }
-        fused_step(st, a, raw, first2, lane);
+        // The stage is refilled by the next TMA.  LDS results arrive asynchronously: issuing them is not enough,
+        // every lane must HOLD its row before the async proxy may overwrite it (observed otherwise: ~1e-3 of frames
+        // corrupted under load).  The vote consumes one word of each LDS.128 -> the scoreboard wait happens there,
+        // and the ballot doubles as the warp-wide rendezvous.  (The magic value never matches on all lanes.)
+        auto refill = [&]() {
+            const uint32_t dep = (raw[0] ^ raw[4] ^ raw[8]) ^ (raw[12] ^ raw[16] ^ raw[20]) ^ raw[24];
+            const unsigned held = __ballot_sync(0xffffffffu, dep != 0x5bd1e995u);
+            if (lane == 0 && a.live1 && held != 0u && p1_live(u1 + 1, w, F)) issue(u1 + 1);
+        };
+        fused_step(st, a, raw, first2, lane, refill);
         __syncthreads();
     }
 }

@@ -82,7 +82,7 @@ extern "C" __attribute__((visibility("default"))) int emu_fused_a64(const uint8_
                         }
                         memcpy(raw, &staged[lane * kRawPitch], kRawPitch);
                     }
-                    fused_step(s->st[w][lane], a, raw, first2, lane);
+                    fused_step(s->st[w][lane], a, raw, first2, lane, [] {});
                 }
             }
         }
