@@ -39,6 +39,15 @@ HASH_BYTES = 32
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
+def measured_traffic_per_frame() -> float | None:
+    """DRAM bytes per frame of the PDQ pipeline from the committed ncu capture (profiles/r01_traffic.json)."""
+    p = ROOT / "profiles" / "r01_traffic.json"
+    try:
+        return float(json.loads(p.read_text())["pdq_pipeline_dram_bytes_per_frame"])
+    except Exception:
+        return None
+
+
 def hbm_peak() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -291,10 +300,15 @@ def run_b200(args) -> None:
         ms_per_step = ms_total / args.steps
         # roofline of the PDQ pipeline (the step's only kernels): algorithmic bytes / device time
         achieved = B * ALGO_BYTES_PER_FRAME / (ms_per_step / 1e3) / 1e9
+        tpf = measured_traffic_per_frame()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src,
-                    "kernel": "PDQ pipeline k1_luma_rowpass+k2_colpass+k3_rowpass_dec+k4_colpass_finalize",
-                    "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME}
+                    "traffic": (tpf * B) if tpf else None, "peak_source": peak_src,
+                    "kernel": "kx_fused_jarosz (91 % of the step) + k4_colpass_finalize<true> (9 %), timed together",
+                    "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_FRAME,
+                    "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
+                    "traffic_source": "profiles/r01_traffic.json (ncu --set full dram__bytes_read+write, per frame x "
+                                      "frames per launch)",
+                    "note": "issue-bound, not HBM-bound: see DESIGN.md 4.2"}
 
         # ---- end to end through the host-pointer C ABI (pinned host memory) ----
         import ctypes as C

@@ -573,18 +573,79 @@ int vpdq_b200_search_host(const uint8_t* h_db, int64_t n_db, const int64_t* h_of
     return rc;
 }
 
+// Per-device scratch of vpdq_b200_match_hash_host, kept between calls (grow-only): the reference calls
+// matchHash once per pair (test_benchmark_vpdqpy.py:49-73), so per-call cudaMalloc / several small copies would
+// dominate.  One pinned staging block [mask | offsets | 64 query hashes | targets] goes down in ONE copy (the
+// zeroed mask word travels with it), one kernel runs, 8 bytes come back.
+namespace {
+struct MatchScratch {
+    cudaStream_t stream = nullptr;
+    uint8_t* h_blk = nullptr;  // pinned
+    uint8_t* d_blk = nullptr;
+    size_t t_cap = 0;          // target capacity in hashes
+    std::mutex mu;
+};
+constexpr size_t kMaskOff = 0, kOffOff = 32, kQOff = 64, kTOff = 64 + 64 * 32;
+MatchScratch g_match[64];
+}  // namespace
+
 int vpdq_b200_match_hash_host(const uint8_t* h_q, int64_t n_q, const uint8_t* h_t, int64_t n_t, int tolerance,
                               double* similarity, int device) {
-    if (!similarity || n_q < 0 || n_t < 0) {
+    if (!similarity || n_q < 0 || n_t < 0 || tolerance < 0) {
         set_error("match_hash: invalid argument");
         return VPDQ_B200_ERR_INVALID;
     }
     *similarity = 0.0;
     if (n_q == 0 || n_t == 0) return VPDQ_B200_OK;  // an empty hash is similar to nothing (DedupeDB.py:555-557)
+    if (!h_q || !h_t) {
+        set_error("match_hash: NULL pointer");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+    int dev = 0;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device index %d out of range", dev);
+        return VPDQ_B200_ERR_INVALID;
+    }
+    MatchScratch& m = g_match[dev];
+    std::lock_guard<std::mutex> lk(m.mu);
+    if (!m.stream) VPDQ_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+    if ((size_t)n_t > m.t_cap) {
+        if (m.d_blk) VPDQ_CUDA(cudaFree(m.d_blk));
+        if (m.h_blk) VPDQ_CUDA(cudaFreeHost(m.h_blk));
+        m.d_blk = nullptr;
+        m.h_blk = nullptr;
+        m.t_cap = 0;
+        size_t cap = 1024;
+        while (cap < (size_t)n_t) cap *= 2;
+        VPDQ_CUDA(cudaMalloc(&m.d_blk, kTOff + cap * 32));
+        VPDQ_CUDA(cudaHostAlloc(&m.h_blk, kTOff + cap * 32, cudaHostAllocDefault));
+        m.t_cap = cap;
+    }
     const int64_t off[2] = {0, n_t};
-    int32_t matched = 0;
-    int rc = vpdq_b200_search_host(h_t, n_t, off, 1, h_q, n_q, tolerance, &matched, device);
-    if (rc) return rc;
+    memcpy(m.h_blk + kOffOff, off, sizeof off);
+    memcpy(m.h_blk + kTOff, h_t, (size_t)n_t * 32);
+    int64_t matched = 0;
+    for (int64_t q0 = 0; q0 < n_q; q0 += 64) {
+        const int nq = (int)(n_q - q0 < 64 ? n_q - q0 : 64);
+        memset(m.h_blk + kMaskOff, 0, 8);
+        memcpy(m.h_blk + kQOff, h_q + q0 * 32, (size_t)nq * 32);
+        // first chunk: everything incl. the targets; later chunks: mask + offsets + queries only
+        const size_t bytes = q0 == 0 ? kTOff + (size_t)n_t * 32 : kTOff;
+        VPDQ_CUDA(cudaMemcpyAsync(m.d_blk, m.h_blk, bytes, cudaMemcpyHostToDevice, m.stream));
+        int rc = hamming_scan_launch(reinterpret_cast<const uint64_t*>(m.d_blk + kTOff), n_t,
+                                     reinterpret_cast<const int64_t*>(m.d_blk + kOffOff), 1,
+                                     reinterpret_cast<const uint64_t*>(m.d_blk + kQOff), nq, tolerance,
+                                     reinterpret_cast<uint64_t*>(m.d_blk + kMaskOff), nullptr, m.stream);
+        if (rc) return rc;
+        VPDQ_CUDA(cudaMemcpyAsync(m.h_blk + kMaskOff, m.d_blk + kMaskOff, 8, cudaMemcpyDeviceToHost, m.stream));
+        VPDQ_CUDA(cudaStreamSynchronize(m.stream));
+        uint64_t mask;
+        memcpy(&mask, m.h_blk + kMaskOff, 8);
+        matched += __builtin_popcountll(mask);
+    }
     *similarity = (100.0 * (double)matched) / (double)n_q;
     return VPDQ_B200_OK;
 }
