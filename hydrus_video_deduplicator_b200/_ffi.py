@@ -48,6 +48,7 @@ PROTOTYPES = {
     "vpdq_b200_abi_version": (C.c_int, []),
     "vpdq_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "vpdq_b200_kernel_launches": (C.c_int, [C.POINTER(C.c_uint64)]),
+    "vpdq_b200_debug_flags": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "vpdq_b200_dct_matrix": (C.c_int, [_f32p]),
     "vpdq_b200_pdq_scratch_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "vpdq_b200_pdq_hash_frames_dev": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
@@ -111,6 +112,12 @@ def kernel_launches() -> int:
     n = C.c_uint64(0)
     check(lib().vpdq_b200_kernel_launches(C.byref(n)))
     return int(n.value)
+
+
+def debug_flags(device: int = 0) -> int:
+    f = C.c_int(0)
+    check(lib().vpdq_b200_debug_flags(int(device), C.byref(f)))
+    return int(f.value)
 
 
 def default_device() -> int:

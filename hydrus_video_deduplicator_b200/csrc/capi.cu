@@ -150,6 +150,15 @@ int vpdq_b200_kernel_launches(uint64_t* count) {
     return VPDQ_B200_OK;
 }
 
+int vpdq_b200_debug_flags(int device, int* flags) {
+    if (!flags) return VPDQ_B200_ERR_INVALID;
+    *flags = 0;
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+    VPDQ_CUDA(cudaDeviceSynchronize());
+    return fused_debug_flags(flags);
+}
+
 int vpdq_b200_device_count(int* count) {
     if (!count) return VPDQ_B200_ERR_INVALID;
     *count = 0;

@@ -40,6 +40,7 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
 // fused luma + Jarosz passes + decimation (pdq_fused.cu): RGB24 frames -> a64 [n][64][64]
 size_t fused_scratch_per_frame();
 int fused_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream);
+int fused_debug_flags(int* flags);
 int pdq_upload_tables();  // DCT matrix -> device (once per device)
 const float* pdq_host_dct();
 

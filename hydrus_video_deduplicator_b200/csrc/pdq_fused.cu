@@ -166,6 +166,14 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// bit 0: an mbarrier wait inside kx_fused_jarosz gave up (a TMA copy never completed) -- never expected
+int fused_debug_flags(int* flags) {
+    int v = 0;
+    VPDQ_CUDA(cudaMemcpyFromSymbol(&v, g_fused_timeout, sizeof v));
+    *flags = v;
+    return VPDQ_B200_OK;
+}
+
 size_t fused_scratch_per_frame() { return (size_t)64 * 64 * sizeof(float); }
 
 // RGB24 frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane

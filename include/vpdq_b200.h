@@ -54,6 +54,9 @@ typedef enum vpdq_b200_status {
 VPDQ_B200_API const char* vpdq_b200_last_error(void);
 VPDQ_B200_API int vpdq_b200_abi_version(void);
 VPDQ_B200_API int vpdq_b200_device_count(int* count);
+/* Self-check after a device synchronise: 0 = healthy; bit 0 = a TMA copy inside the fused PDQ kernel never
+ * completed (its bounded wait gave up) -- results of that launch are then invalid. */
+VPDQ_B200_API int vpdq_b200_debug_flags(int device, int* flags);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 VPDQ_B200_API int vpdq_b200_kernel_launches(uint64_t* count);
 /* the 16 x 64 fp32 DCT table the kernels use (host copy; bit-identical to the oracle's) */

@@ -175,3 +175,6 @@ def test_fused_kernel_is_deterministic_under_load(torch_dev):
     for _ in range(4):
         h, q, a, _ = device.hash_frames(frames, stages=True)
         assert torch.equal(a, a0) and torch.equal(h, h0) and torch.equal(q, q0)
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    assert _ffi.debug_flags(0) == 0  # no TMA wait ever timed out
