@@ -36,7 +36,14 @@ sys.path.insert(0, str(ROOT))
 FRAME_BYTES = 512 * 512 * 3
 ALGO_BYTES_PER_FRAME = FRAME_BYTES + 32 + 4  # RGB24 in, hash + quality out
 HASH_BYTES = 32
+_REAL_STDOUT = None
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def measured_traffic_per_frame() -> float | None:
@@ -227,7 +234,7 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def hash_config(args, frames_per_step: int) -> dict:
@@ -349,6 +356,8 @@ def run_b200(args) -> None:
 
         if rank == 0 and world == 1 and not args.no_hamming:
             extra["hamming"] = hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args)
+        if rank == 0 and world == 1 and not args.no_luma:
+            extra["luma_frames"] = luma_section(torch, dev_api, dev, local, args)
     else:
         # ---- all-pairs Hamming, DB sharded over ranks, all_gather of candidate bitmaps ----
         nt, nq = args.shard_hashes, args.query_block
@@ -423,7 +432,7 @@ def run_b200(args) -> None:
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, pool[0] if args.workload == "hash" else None, torch)
     line.update(extra)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(args, pool0, torch) -> dict:
@@ -447,6 +456,47 @@ def cpu_baseline(args, pool0, torch) -> dict:
     rate, secs = cpu_pairs_rate(16384, cores)
     return {"value": rate, "unit": "pair-comparisons/s", "cores": cores, "kind": "port",
             "sample": f"16384 x 16384 hashes on {cores} threads ({secs:.1f} s)"}
+
+
+def luma_section(torch, dev_api, dev, local, args) -> dict:
+    """BASELINE's "512x512 luma frames" variant: 8-bit gray input, DEFINED as the RGB frame R=G=B=L (SURVEY.md note
+    a-1; one byte per pixel crosses PCIe instead of three).  Uses the v1 line kernels (csrc/pdq_kernels.cu)."""
+    import ctypes as C
+
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    n = min(args.batch, 2048)
+    g = torch.Generator(device=dev).manual_seed(4242)
+    gray = torch.randint(0, 256, (n, 512, 512), dtype=torch.uint8, device=dev, generator=g)
+    for _ in range(2):
+        dev_api.hash_frames(gray)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        h, q = dev_api.hash_frames(gray)
+    b.record()
+    torch.cuda.synchronize()
+    dev_rate = 5 * n / (a.elapsed_time(b) / 1e3)
+    hg = torch.empty((n, 512, 512), dtype=torch.uint8, pin_memory=True)
+    hg.copy_(gray)
+    hh = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
+    hq = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step():
+        _ffi.check(_ffi.lib().vpdq_b200_pdq_hash_frames_host(C.c_void_p(hg.data_ptr()), 1, n, 512, 512,
+                                                             C.c_void_p(hh.data_ptr()), C.c_void_p(hq.data_ptr()), local))
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step()
+    e2e_rate = 5 * n / (time.perf_counter() - t0)
+    rgb = gray[:4].unsqueeze(-1).expand(-1, -1, -1, 3).contiguous()
+    same = bool(torch.equal(dev_api.hash_frames(rgb)[0], h[:4]) and torch.equal(hh[:4], h[:4].cpu()))
+    return {"frames_per_s_device_resident": dev_rate, "frames_per_s_e2e": e2e_rate, "frames": n,
+            "bytes_per_frame": 512 * 512, "equals_rgb_expansion": same,
+            "kernels": "k1_luma_rowpass<1> + k2_colpass + k3_rowpass_dec + k4_colpass_finalize<false>"}
 
 
 def hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args) -> dict:
@@ -509,6 +559,12 @@ def hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args) -> dict
 
 
 def main() -> None:
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter) is sent to stderr, and the line is written to the real stdout at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=25)
@@ -524,6 +580,7 @@ def main() -> None:
     ap.add_argument("--shard-hashes", type=int, default=1_250_000)
     ap.add_argument("--query-block", type=int, default=262_144)
     ap.add_argument("--no-hamming", action="store_true")
+    ap.add_argument("--no-luma", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

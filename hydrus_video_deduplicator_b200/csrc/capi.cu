@@ -296,6 +296,20 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
     return rc;
 }
 
+int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width, uint8_t* d_dst,
+                               void* stream) {
+    if (n_frames < 0 || src_height < 1 || src_width < 1 || src_height > 32768 || src_width > 32768) {
+        set_error("point_resize: invalid argument (n=%lld, %dx%d)", (long long)n_frames, src_width, src_height);
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (n_frames == 0) return VPDQ_B200_OK;
+    if (!d_src || !d_dst || ((uintptr_t)d_dst & 3)) {
+        set_error("point_resize: NULL pointer or destination not 4-byte aligned");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return point_resize_launch(d_src, n_frames, src_height, src_width, d_dst, (cudaStream_t)stream);
+}
+
 // ---- hasher handle -----------------------------------------------------------------------------------
 int vpdq_b200_hasher_create(int device, int width, int height, int channels, int num_threads,
                             vpdq_b200_hasher** out) {

@@ -44,6 +44,10 @@ int fused_debug_flags(int* flags);
 int pdq_upload_tables();  // DCT matrix -> device (once per device)
 const float* pdq_host_dct();
 
+// ---- POINT resize (resize_kernels.cu) ----------------------------------------------------------------
+int point_resize_launch(const uint8_t* d_src, int64_t n_frames, int src_h, int src_w, uint8_t* d_dst,
+                        cudaStream_t stream);
+
 // ---- Hamming (hamming_kernels.cu) ---------------------------------------------------------------
 int hamming_scan_launch(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets, int64_t n_videos,
                         const uint64_t* d_query, int n_query, int tol, uint64_t* d_qmask, int32_t* d_tcount,

@@ -68,6 +68,24 @@ def hash_frames(frames: torch.Tensor, *, stages: bool = False):
     return hashes, quality
 
 
+def point_resize(frames: torch.Tensor) -> torch.Tensor:
+    """[n, H, W, 3] uint8 CUDA (natively sized decoded frames) -> [n, 512, 512, 3]: the reference's
+    frame.reformat(512, 512, "rgb24", POINT) (vpdqpy.py:90-95) on the device."""
+    frames = _need_cuda(frames, "frames", torch.uint8)
+    if frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError("frames must be [n, H, W, 3]")
+    n, h, w = frames.shape[:3]
+    out = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _ffi.check(_ffi.lib().vpdq_b200_point_resize_dev(frames.data_ptr(), n, h, w, out.data_ptr(), _stream_ptr()))
+    return out
+
+
+def hash_native_frames(frames: torch.Tensor):
+    """POINT-resize + hash natively sized RGB frames without leaving the device."""
+    return hash_frames(point_resize(frames))
+
+
 def _as_hash_matrix(t: torch.Tensor, name: str) -> torch.Tensor:
     """[n, 32] uint8 or [n, 4] int64 -> contiguous CUDA tensor, 32-byte rows"""
     if not t.is_cuda:

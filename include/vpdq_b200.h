@@ -82,6 +82,12 @@ VPDQ_B200_API int vpdq_b200_pdq_stages_dev(const uint8_t* d_frames, int channels
                              uint8_t* d_hashes, int32_t* d_quality, float* d_a64, float* d_b16, void* d_scratch,
                              size_t scratch_bytes, void* stream);
 
+/* The reference's frame.reformat(width=512, height=512, format="rgb24", interpolation=POINT)
+ * (vpdqpy.py:90-95) on the device: d_src [n][src_height][src_width][3] u8 -> d_dst [n][512][512][3] u8,
+ * swscale's centre-based nearest neighbour.  Stream-ordered, no allocation. */
+VPDQ_B200_API int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width,
+                                             uint8_t* d_dst, void* stream);
+
 /* One-shot host call: h_frames -> h_hashes/h_quality, copies included (pinned or pageable memory). */
 VPDQ_B200_API int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_t n_frames, int width, int height,
                                    uint8_t* h_hashes, int32_t* h_quality, int device);

@@ -94,6 +94,12 @@ def test_world_size_2_gloo(tmp_path):
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
 
+def test_cpulist_parsing():
+    assert hdist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hdist._parse_cpulist("") == set()
+    assert hdist.bind_to_gpu_numa_node(0) is None or isinstance(hdist.bind_to_gpu_numa_node(0), int)
+
+
 def test_popcount64():
     x = torch.tensor([0, 1, -1, 0x00FF00FF00FF00FF, 1 << 62, -(1 << 63)], dtype=torch.int64)
     assert hdist.popcount64(x).tolist() == [0, 1, 64, 32, 1, 1]

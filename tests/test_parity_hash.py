@@ -38,6 +38,23 @@ def test_gif_known_answer_on_gpu(golden_dir, torch_dev):
     assert (quality == 100).all()
 
 
+def test_device_point_resize_and_native_hash(golden_dir, torch_dev):
+    """8f-2: swscale POINT resize on the device == the host index rule, for several native sizes; and the golden
+    GIF clip hashed from its NATIVE 360x640 frames entirely on the device reproduces the reference's hashes."""
+    torch, dev = torch_dev
+    from hydrus_video_deduplicator_b200 import device
+
+    rng = np.random.default_rng(2)
+    for h, w in ((360, 640), (1080, 1920), (64, 48), (512, 512), (719, 1281), (2160, 3840)):
+        src = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        got = device.point_resize(torch.from_numpy(src).to(dev)).cpu().numpy()
+        assert got.tobytes() == np.stack([point_resize_rgb(f) for f in src]).tobytes(), (h, w)
+    native = np.load(golden_dir / "bbb_gif_frames.npz")["frames"]
+    hashes, quality = device.hash_native_frames(torch.from_numpy(native).to(dev))
+    gold = bytes.fromhex((golden_dir / "video_hashes" / "S01_Big_Buck_Bunny_360_10s.gif.txt").read_text().strip())
+    assert hashes.cpu().numpy().tobytes() == gold and (quality.cpu().numpy() == 100).all()
+
+
 def test_stages_bit_exact_vs_oracle(torch_dev):
     """The 64x64 decimated plane and the 16x16 DCT must match the oracle to the last bit: this is what
     pins the fp32 operation order (no FMA contraction, sequential running sums)."""

@@ -44,6 +44,8 @@ def main():
     rank, world, local = hdist.init()
     dev = torch.device("cuda", local)
     mine = hdist.round_robin(args.clips, world, rank)
+    device.hash_frames(clip_frames(0, args.clips, min(args.frames, 32), dev))  # warm-up: module load, attributes
+    torch.cuda.synchronize()
     t_hash = 0.0
     local_hashes = torch.zeros((len(mine), args.frames, 32), dtype=torch.uint8, device=dev)
     local_quality = torch.zeros((len(mine), args.frames), dtype=torch.int32, device=dev)
