@@ -55,6 +55,7 @@ PROTOTYPES = {
                                                 C.c_size_t, _vp]),
     "vpdq_b200_pdq_stages_dev": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                            C.c_size_t, _vp]),
+    "vpdq_b200_pdq_jarosz_dev": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]),
     "vpdq_b200_point_resize_dev": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp]),
     "vpdq_b200_pdq_hash_frames_host": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "vpdq_b200_hasher_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),

@@ -296,6 +296,18 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
     return rc;
 }
 
+int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int width, int height, float* d_a64,
+                             void* stream) {
+    int rc = check_frames(d_frames, 3, n_frames, width, height);
+    if (rc) return rc;
+    if (n_frames == 0) return VPDQ_B200_OK;
+    if (!d_a64 || ((uintptr_t)d_frames & 15) || ((uintptr_t)d_a64 & 15)) {
+        set_error("pdq_jarosz: NULL output or pointers not 16-byte aligned");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream);
+}
+
 int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width, uint8_t* d_dst,
                                void* stream) {
     if (n_frames < 0 || src_height < 1 || src_width < 1 || src_height > 32768 || src_width > 32768) {

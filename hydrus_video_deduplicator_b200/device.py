@@ -68,6 +68,19 @@ def hash_frames(frames: torch.Tensor, *, stages: bool = False):
     return hashes, quality
 
 
+def jarosz_planes(frames: torch.Tensor) -> torch.Tensor:
+    """[n, 512, 512, 3] uint8 CUDA -> [n, 64, 64] f32: the Jarosz-filtered, decimated luma plane (the fused kernel
+    on its own; hash_frames = this + the finalize kernel)."""
+    frames = _need_cuda(frames, "frames", torch.uint8)
+    if frames.dim() != 4 or frames.shape[1:] != (512, 512, 3):
+        raise ValueError("frames must be [n, 512, 512, 3]")
+    out = torch.empty((frames.shape[0], 64, 64), dtype=torch.float32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _ffi.check(_ffi.lib().vpdq_b200_pdq_jarosz_dev(frames.data_ptr(), frames.shape[0], 512, 512, out.data_ptr(),
+                                                       _stream_ptr()))
+    return out
+
+
 def point_resize(frames: torch.Tensor) -> torch.Tensor:
     """[n, H, W, 3] uint8 CUDA (natively sized decoded frames) -> [n, 512, 512, 3]: the reference's
     frame.reformat(512, 512, "rgb24", POINT) (vpdqpy.py:90-95) on the device."""

@@ -82,6 +82,12 @@ VPDQ_B200_API int vpdq_b200_pdq_stages_dev(const uint8_t* d_frames, int channels
                              uint8_t* d_hashes, int32_t* d_quality, float* d_a64, float* d_b16, void* d_scratch,
                              size_t scratch_bytes, void* stream);
 
+/* First half of the frame hash on its own: RGB24 frames -> the Jarosz-filtered, decimated 64x64 luma plane
+ * d_a64 [n][64][64] f32 (PDQ's "buffer64x64", the input of the quality metric and the DCT).  This is exactly the
+ * fused kernel kx_fused_jarosz; bench.py times it alone for the roofline of the dominant kernel. */
+VPDQ_B200_API int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int width, int height,
+                                           float* d_a64, void* stream);
+
 /* The reference's frame.reformat(width=512, height=512, format="rgb24", interpolation=POINT)
  * (vpdqpy.py:90-95) on the device: d_src [n][src_height][src_width][3] u8 -> d_dst [n][512][512][3] u8,
  * swscale's centre-based nearest neighbour.  Stream-ordered, no allocation. */

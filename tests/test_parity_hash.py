@@ -68,6 +68,30 @@ def test_stages_bit_exact_vs_oracle(torch_dev):
         assert hashes[k].tobytes() == h.tobytes() and quality[k] == q
 
 
+def test_jarosz_planes_entry_point(torch_dev):
+    torch, dev = torch_dev
+    from hydrus_video_deduplicator_b200 import device
+
+    frames = synth.synth_frames(5, seed=33)
+    planes = device.jarosz_planes(torch.from_numpy(frames).to(dev)).cpu().numpy()
+    for k in range(5):
+        assert planes[k].tobytes() == oracle.pdq_stages(frames[k])[2].tobytes()
+
+
+def test_two_hashers_interleaved():
+    """Two VideoHashers fed alternately (each owns its stream, ring and scratch): no cross-talk."""
+    fa, fb = synth.synth_frames(70, seed=50), synth.synth_frames(45, seed=51)
+    ha, hb = vpdq.VideoHasher(1, 512, 512, 0), vpdq.VideoHasher(1, 512, 512, 4)
+    for k in range(70):
+        ha.hash_frame(fa[k].tobytes())
+        if k < 45:
+            hb.hash_frame(fb[k].tobytes())
+    assert ha.finish().bytes == oracle.video_hash(fa, nthreads=8)
+    assert hb.finish().bytes == oracle.video_hash(fb, nthreads=8)
+    ha.close()
+    hb.close()
+
+
 @pytest.mark.parametrize("channels", [3, 1])
 def test_synthetic_frames_bit_exact(torch_dev, channels):
     torch, dev = torch_dev
