@@ -46,11 +46,19 @@ def emit(line: dict) -> None:
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+def jarosz_kernel_name() -> str:
+    """The Jarosz kernel the library runs for RGB24 frames (csrc/pdq_kernels.cu pdq_impl())."""
+    return {"fused": "kx_fused_jarosz", "lines": "k1_luma_rowpass+k2_colpass+k3_rowpass_dec"}.get(
+        os.environ.get("VPDQ_B200_PDQ_IMPL", ""), "kx_fused_jarosz2")
+
+
 def measured_traffic_per_frame() -> float | None:
-    """DRAM bytes per frame of the PDQ pipeline from the committed ncu capture (profiles/r01_traffic.json)."""
+    """DRAM bytes per frame of the dominant PDQ kernel from the committed ncu capture (profiles/r01_traffic.json)."""
     p = ROOT / "profiles" / "r01_traffic.json"
     try:
-        return float(json.loads(p.read_text())["pdq_pipeline_dram_bytes_per_frame"])
+        d = json.loads(p.read_text())
+        k = d[jarosz_kernel_name()]
+        return (float(k["dram_read_bytes"]) + float(k["dram_write_bytes"])) / float(k["frames"])
     except Exception:
         return None
 
@@ -305,7 +313,7 @@ def run_b200(args) -> None:
         launches = _ffi.kernel_launches() - launches0
         value = world * B * args.steps / (ms_total / 1e3)
         ms_per_step = ms_total / args.steps
-        # the dominant kernel alone (kx_fused_jarosz = vpdq_b200_pdq_jarosz_dev), CUDA events per launch
+        # the dominant kernel alone (kx_fused_jarosz2 = vpdq_b200_pdq_jarosz_dev), CUDA events per launch
         a64 = torch.empty((B, 64, 64), dtype=torch.float32, device=dev)
         kx_ms = []
         stream = torch.cuda.current_stream().cuda_stream
@@ -326,9 +334,9 @@ def run_b200(args) -> None:
         tpf = measured_traffic_per_frame()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (tpf * B) if tpf else None, "peak_source": peak_src,
-                    "kernel": "kx_fused_jarosz", "kernel_ms_per_launch": kx_ms,
+                    "kernel": jarosz_kernel_name(), "kernel_ms_per_launch": kx_ms,
                     "kernel_share_of_step": kx_ms / ms_per_step,
-                    "pipeline": {"kernels": "kx_fused_jarosz + k4_colpass_finalize<true>", "achieved": pipeline_gbs,
+                    "pipeline": {"kernels": jarosz_kernel_name() + " + k4_colpass_finalize<true>", "achieved": pipeline_gbs,
                                  "frac": pipeline_gbs / peak},
                     "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_FRAME,
                     "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,

@@ -156,8 +156,17 @@ int vpdq_b200_debug_flags(int device, int* flags) {
     DeviceGuard g(device);
     if (g.rc) return g.rc;
     VPDQ_CUDA(cudaDeviceSynchronize());
-    return fused_debug_flags(flags);
+    int f1 = 0, f2 = 0;
+    int rc = fused_debug_flags(&f1);
+    if (rc) return rc;
+    rc = fused2_debug_flags(&f2);
+    if (rc) return rc;
+    *flags = f1 | f2;
+    return VPDQ_B200_OK;
 }
+
+int vpdq_b200_set_pdq_impl(int impl) { return pdq_set_impl(impl); }
+int vpdq_b200_get_pdq_impl(void) { return pdq_impl(); }
 
 int vpdq_b200_device_count(int* count) {
     if (!count) return VPDQ_B200_ERR_INVALID;
@@ -305,7 +314,8 @@ int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int widt
         set_error("pdq_jarosz: NULL output or pointers not 16-byte aligned");
         return VPDQ_B200_ERR_INVALID;
     }
-    return fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream);
+    return pdq_impl() == 1 ? fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream)
+                           : fused2_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream);
 }
 
 int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width, uint8_t* d_dst,

@@ -331,20 +331,35 @@ size_t pdq_scratch_bytes(int64_t n_frames) {
     return (size_t)c * kScratchPerFrame;
 }
 
-// which pipeline hashes RGB frames: the fused kernel (default) or the v1 line kernels
-// (VPDQ_B200_PDQ_IMPL=lines; both are CUDA and bit-identical -- the switch exists for A/B measurements)
-static bool use_fused() {
-    static const bool fused = [] {
+// which pipeline hashes RGB frames: the frame-pair fused kernel (default), the one-frame fused kernel
+// (VPDQ_B200_PDQ_IMPL=fused) or the v1 line kernels (=lines); all are CUDA and bit-identical -- the switch
+// exists for A/B measurements
+static std::atomic<int> g_pdq_impl{-1};
+
+int pdq_impl() {
+    int v = g_pdq_impl.load(std::memory_order_relaxed);
+    if (v < 0) {
         const char* e = getenv("VPDQ_B200_PDQ_IMPL");
-        return !(e && strcmp(e, "lines") == 0);
-    }();
-    return fused;
+        v = (e && strcmp(e, "lines") == 0) ? 0 : (e && strcmp(e, "fused") == 0) ? 1 : 2;
+        g_pdq_impl.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+int pdq_set_impl(int impl) {
+    if (impl < 0 || impl > 2) {
+        set_error("set_pdq_impl: %d is not one of 0 (lines), 1 (fused), 2 (fused2)", impl);
+        return VPDQ_B200_ERR_INVALID;
+    }
+    g_pdq_impl.store(impl, std::memory_order_relaxed);
+    return VPDQ_B200_OK;
 }
 
 int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t* d_hashes, int32_t* d_quality,
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (n_frames == 0) return VPDQ_B200_OK;
-    const bool fused = channels == 3 && use_fused();
+    const int impl = channels == 3 ? pdq_impl() : 0;
+    const bool fused = impl != 0;
     const size_t per_frame = fused ? fused_scratch_per_frame() : kScratchPerFrame;
     int64_t chunk = (int64_t)(scratch_bytes / per_frame);
     if (chunk < 1) {
@@ -365,7 +380,7 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
         float* bdbg = d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr;
         if (fused) {
             float* a64 = static_cast<float*>(d_scratch);
-            rc = fused_jarosz_launch(src, nf, a64, stream);
+            rc = impl == 2 ? fused2_jarosz_launch(src, nf, a64, stream) : fused_jarosz_launch(src, nf, a64, stream);
             if (rc) return rc;
             k4_colpass_finalize<true><<<(unsigned)nf, 256, 0, stream>>>(a64, hp, qp, adbg, bdbg);
         } else {

@@ -57,6 +57,12 @@ VPDQ_B200_API int vpdq_b200_device_count(int* count);
 /* Self-check after a device synchronise: 0 = healthy; bit 0 = a TMA copy inside the fused PDQ kernel never
  * completed (its bounded wait gave up) -- results of that launch are then invalid. */
 VPDQ_B200_API int vpdq_b200_debug_flags(int device, int* flags);
+/* Which CUDA pipeline hashes RGB24 frames (all bit-identical; for A/B measurements and cross-checks):
+ * 2 = frame-pair fused kernel kx_fused_jarosz2 (default), 1 = one-frame fused kernel kx_fused_jarosz,
+ * 0 = v1 line kernels.  Initial value from the environment variable VPDQ_B200_PDQ_IMPL (fused | lines).
+ * set returns VPDQ_B200_ERR_INVALID for any other value; get returns the current one. */
+VPDQ_B200_API int vpdq_b200_set_pdq_impl(int impl);
+VPDQ_B200_API int vpdq_b200_get_pdq_impl(void);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 VPDQ_B200_API int vpdq_b200_kernel_launches(uint64_t* count);
 /* the 16 x 64 fp32 DCT table the kernels use (host copy; bit-identical to the oracle's) */

@@ -39,6 +39,30 @@ def test_emulated_schedule_is_bit_exact(emu, n_frames, grid):
         assert a64[f].tobytes() == a_ref.tobytes(), f"frame {f}: decimated plane differs from the oracle"
 
 
+@pytest.fixture(scope="module")
+def emu2():
+    so = EMU_DIR / "libpdq_fused2_emu.so"
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so),
+                    str(EMU_DIR / "pdq_fused2_emu.cpp")], check=True)
+    lib = C.CDLL(str(so))
+    lib.emu_fused2_a64.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("n_frames,grid", [(1, 1), (2, 1), (3, 1), (6, 1), (5, 2), (4, 7), (9, 2)])
+def test_emulated_pair_schedule_is_bit_exact(emu2, n_frames, grid):
+    """kx_fused_jarosz2 (two frames per lane, 8 main warps + the P4 warp, deferred power-of-two scaling): odd and
+    even frame counts per CTA (half B one frame shorter), a single frame (half B empty), empty CTAs."""
+    frames = synth.synth_frames(n_frames, seed=57 + n_frames)
+    a64 = np.full((n_frames, 64, 64), np.nan, np.float32)
+    errors = emu2.emu_fused2_a64(frames.ctypes.data_as(C.c_void_p), n_frames, grid, a64.ctypes.data_as(C.c_void_p))
+    assert errors == 0
+    assert not np.isnan(a64).any(), "some decimated outputs were never written (or were fed poison)"
+    for f in range(n_frames):
+        _, _, a_ref, _ = oracle.pdq_stages(frames[f])
+        assert a64[f].tobytes() == a_ref.tobytes(), f"frame {f}: decimated plane differs from the oracle"
+
+
 def test_div3_is_exact(tmp_path):
     exe = tmp_path / "div3_check"
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), str(EMU_DIR / "div3_check.c"), "-lm"], check=True)

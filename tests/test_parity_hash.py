@@ -219,3 +219,32 @@ def test_fused_kernel_is_deterministic_under_load(torch_dev):
     from hydrus_video_deduplicator_b200 import _ffi
 
     assert _ffi.debug_flags(0) == 0  # no TMA wait ever timed out
+
+
+@pytest.mark.parametrize("n_frames", [1, 2, 3, 147, 149, 297, 1000])
+def test_three_cuda_pipelines_agree(torch_dev, n_frames):
+    """kx_fused_jarosz2 (frame pairs, default), kx_fused_jarosz and the v1 line kernels give identical decimated
+    planes, hashes and quality -- for frame counts that leave CTAs with 0, 1, odd and even numbers of frames --
+    and the default equals the oracle on a strided sample."""
+    torch, dev = torch_dev
+    from bench import device_frames
+    from hydrus_video_deduplicator_b200 import _ffi, device
+
+    frames = device_frames(torch, n_frames, dev, seed=900 + n_frames)
+    out = {}
+    try:
+        for impl in ("fused2", "fused", "lines"):
+            _ffi.set_pdq_impl(impl)
+            assert _ffi.get_pdq_impl() == impl
+            out[impl] = device.hash_frames(frames, stages=True)
+    finally:
+        _ffi.set_pdq_impl("fused2")
+    torch.cuda.synchronize()
+    for impl in ("fused", "lines"):
+        for got, want in zip(out[impl][:3], out["fused2"][:3]):
+            assert torch.equal(got, want), impl
+    idx = list(range(0, n_frames, max(1, n_frames // 12)))
+    ref_h, ref_q = oracle.pdq_hash_frames(frames[idx].cpu().numpy(), nthreads=8)
+    assert out["fused2"][0][idx].cpu().numpy().tobytes() == ref_h.tobytes()
+    assert (out["fused2"][1][idx].cpu().numpy() == ref_q).all()
+    assert _ffi.debug_flags(0) == 0
