@@ -122,7 +122,8 @@ constexpr int kPitch = kTile + 2;                 // F2 per tile row (272 B = 17
 constexpr int kSlotF2 = kTile * kPitch;           // 1088 F2 = 8704 B per tile slot
 constexpr int kT3Pitch = kTile + 4;               // F2 per decimated column in t3 (+4: the 4 columns of a strip
                                                   // read by the P4 warp land in different banks)
-constexpr int kT3Strip = 4 * kT3Pitch;            // F2 per strip in a t3 buffer: [q = 0..3][row 0..31]
+constexpr int kT3Strip = 4 * kT3Pitch + 2;        // F2 per strip in a t3 buffer: [q = 0..3][row 0..31]; +2 (16 B): the
+                                                  // P4 warp's 8 strips x 4 columns 128-bit reads are conflict free
 constexpr int kTStart = -8;                       // first step (warp 7's P1 on the virtual pair -1)
 
 // running-sum box filter, window 4, two frames at once: feeding x[r] returns
@@ -211,11 +212,12 @@ VPDQ2_HD void swap_f2(F2& a, F2& b) { const F2 t = a; a = b; b = t; }
 // One lane's work for one step of a main warp: the three roles, interleaved element by element.
 // raw_a / raw_b: the lane's staged RGB rows of the two frames (28 words, pixels from byte kRawSkip);
 // first_a / first_b: bytes 0..7 of those image rows (pixels 0, 1; used when s1 == 0).
-// after_loads(): called once the step's up-front shared-memory loads have been issued.
-template <typename Hook>
+// (The kernel pulls them into registers at the END of the previous step and hands the staging buffers back to
+// TMA at once, so that the copy for the step after next has a whole step to land.)
+template <int V = 0>
 VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a)[kRawWords],
                         const uint32_t (&raw_b)[kRawWords], const uint32_t (&first_a)[2],
-                        const uint32_t (&first_b)[2], int lane, Hook after_loads) {
+                        const uint32_t (&first_b)[2], int lane) {
     // ---- per-role prologues (warp-uniform conditions) ----
     if (a.swap2) {
         swap_chain(st.c2, st.c2_parked);
@@ -241,14 +243,13 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
         const F4 v0 = *reinterpret_cast<const F4*>(row_a), v1 = *reinterpret_cast<const F4*>(row_a + 2);
         x3[0][0] = v0.lo; x3[0][1] = v0.hi; x3[0][2] = v1.lo; x3[0][3] = v1.hi;
     }
-    F2 x2_next = col_b[0];
-    after_loads();
+    F2 x2_q[2] = {col_b[0], col_b[kPitch]};  // P2's input, fetched two rows ahead
     F2 n0{0.0f, 0.0f}, n1{0.0f, 0.0f};
     F2 y1[4];
 
     VPDQ2_UNROLL
     for (int k = 0; k < kTile; ++k) {
-        if ((k & 3) == 0 && k + 4 < kTile) {  // P3's next chunk (columns k+4..k+7): P1 stores there at k+7
+        if ((k & 3) == 0 && k + 4 < kTile && !(V & 4)) {  // P3's next chunk (columns k+4..k+7): P1 stores there at k+7
             const F4 v0 = *reinterpret_cast<const F4*>(row_a + k + 4), v1 = *reinterpret_cast<const F4*>(row_a + k + 6);
             F2(&dst)[4] = x3[((k >> 2) + 1) & 1];
             dst[0] = v0.lo; dst[1] = v0.hi; dst[2] = v1.lo; dst[3] = v1.hi;
@@ -260,17 +261,18 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
         }
         // P1: luma + row pass 1, fed pixel 32*s1 + 2 + k -> output column 32*s1 + k
         {
-            const F2 v = st.c1.feed(luma_pair_at(raw_a, raw_b, kRawSkip + 3 * k));
+            const F2 v = st.c1.feed((V & 1) ? F2{bits_to_float(raw_a[(kRawSkip + 3 * k) >> 2]), bits_to_float(raw_b[(kRawSkip + 3 * k) >> 2])}
+                                            : luma_pair_at(raw_a, raw_b, kRawSkip + 3 * k));
             y1[k & 3] = edge_scale(v, k, a.s1);
-            if ((k & 3) == 3 && a.live1) {
+            if ((k & 3) == 3 && a.live1 && !(V & 64)) {
                 *reinterpret_cast<F4*>(row_a + k - 3) = F4{y1[0], y1[1]};
                 *reinterpret_cast<F4*>(row_a + k - 1) = F4{y1[2], y1[3]};
             }
         }
         // P2: column pass 1 in place, fed P1 row 32*b2 + 2 + k -> output row 32*b2 + k
-        {
-            F2 x2 = x2_next;
-            if (k + 1 < kTile) x2_next = col_b[(k + 1) * kPitch];
+        if (!(V & 2)) {
+            F2 x2 = x2_q[k & 1];
+            if (k + 2 < kTile) x2_q[k & 1] = col_b[(k + 2) * kPitch];
             if (k == 30) n0 = x2;
             if (k == 31) n1 = x2;
             if (k >= 30 && a.b2 == 15) x2 = F2{0.0f, 0.0f};  // image rows 512, 513 do not exist: the two drain steps

@@ -18,6 +18,8 @@ struct Cta {
     alignas(16) F2 t3[2][kMainWarps * kT3Strip];
     uint8_t raw[kMainWarps][2][kRawBoxBytes];
     int raw_holds[kMainWarps];  // which tile index u is staged (checks the ring protocol)
+    uint8_t regs[kMainWarps][2][kRawBoxBytes];  // the staged rows as held in the lanes' registers
+    int regs_hold[kMainWarps];
 };
 
 void tma_box(const uint8_t* frames, long long total_rows, int x, long long y, uint8_t* dst) {
@@ -52,6 +54,7 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
         for (int w = 0; w < kMainWarps; ++w) {
             for (int l = 0; l < 32; ++l) s->st[w][l].init();
             s->raw_holds[w] = -1000;
+            s->regs_hold[w] = -1000;
         }
         for (int l = 0; l < 32; ++l) s->p4[l].init();
         auto issue = [&](int u, int w) {
@@ -59,8 +62,17 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
             tma_box(frames, total_rows, p1_box_x(u), p1_row0(half_b, u, w), &s->raw[w][1][0]);
             s->raw_holds[w] = u;
         };
-        for (int w = 0; w < kMainWarps; ++w)
+        // pull the staged rows of tile u into "registers" one step ahead, then hand the stage back for tile u + 1
+        auto load_stage = [&](int u, int w) {
+            if (s->raw_holds[w] != u) ++errors;  // ring protocol violated
+            memcpy(s->regs[w], s->raw[w], sizeof s->regs[w]);  // every lane reads its rows BEFORE the refill
+            s->regs_hold[w] = u;
+            if (p1_live(u + 1, w, FA)) issue(u + 1, w);
+        };
+        for (int w = 0; w < kMainWarps; ++w) {
             if (p1_live(p1_first(w), w, FA)) issue(p1_first(w), w);
+            if (sched_u(kTStart, 1, w) == p1_first(w) && p1_live(p1_first(w), w, FA)) load_stage(p1_first(w), w);
+        }
         const int t_last = last_step(FA);
         for (int T = kTStart; T <= t_last; ++T) {
             bool b_touched[kMainWarps] = {}, t3_touched[kMainWarps] = {};
@@ -79,10 +91,8 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
                 a.t3_w = s->t3[T & 1] + (a.s3 & 7) * kT3Strip;
                 if (a.live2) { if (b_touched[a.b2 & 7]) ++errors; b_touched[a.b2 & 7] = true; }
                 if (a.live3) { if (t3_touched[a.s3 & 7]) ++errors; t3_touched[a.s3 & 7] = true; }
-                if (a.live1 && s->raw_holds[w] != u1) ++errors;  // ring protocol violated
-                uint8_t staged[2][kRawBoxBytes];
-                memcpy(staged, s->raw[w], sizeof staged);  // every lane reads its rows BEFORE the refill
-                if (a.live1 && p1_live(u1 + 1, w, FA)) issue(u1 + 1, w);
+                if (a.live1 && s->regs_hold[w] != u1) ++errors;  // the registers must hold this step's rows
+                const uint8_t (&staged)[2][kRawBoxBytes] = s->regs[w];
                 for (int lane = 0; lane < 32; ++lane) {
                     uint32_t first_a[2] = {0, 0}, first_b[2] = {0, 0};
                     uint32_t raw_a[kRawWords], raw_b[kRawWords];
@@ -97,8 +107,9 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
                         memcpy(raw_a, &staged[0][lane * kRawPitch], kRawPitch);
                         memcpy(raw_b, &staged[1][lane * kRawPitch], kRawPitch);
                     }
-                    main_step(s->st[w][lane], a, raw_a, raw_b, first_a, first_b, lane, [] {});
+                    main_step(s->st[w][lane], a, raw_a, raw_b, first_a, first_b, lane);
                 }
+                if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1, w);
             }
             for (int lane = 0; lane < 32; ++lane) {  // the P4 warp
                 const int g = lane >> 2, q = lane & 3;
