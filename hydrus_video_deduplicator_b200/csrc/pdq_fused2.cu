@@ -16,7 +16,6 @@
 #include <cuda.h>
 
 #include <mutex>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "pdq_fused2_core.h"
@@ -80,7 +79,6 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(kFused2Threads) : "memory"); }
 }  // namespace
 
-template <int V>
 __global__ void __launch_bounds__(kFused2Threads, 1)
     kx_fused_jarosz2(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames,
                      long long n_frames_total, float* __restrict__ a64) {
@@ -121,8 +119,8 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
             const int col = 4 * col_strip(u4, g) + q;
             a.out_a = a64 + (size_t)(half_a + n) * 4096 + col;
             a.out_b = a64 + (size_t)(a.live_b ? half_b + n : half_a + n) * 4096 + col;
-            if (!(V & 32)) p4_step(st, a);
-            if (!(V & 8)) cta_barrier();
+            p4_step(st, a);
+            cta_barrier();
         }
         return;
     }
@@ -134,7 +132,7 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
         tma_load_2d(&sm.raw[w][0][0], &tmap, p1_box_x(u), (int)p1_row0(half_a, u, w), &sm.bar[w]);
         tma_load_2d(&sm.raw[w][1][0], &tmap, p1_box_x(u), (int)p1_row0(half_b, u, w), &sm.bar[w]);
     };
-    if (lane == 0 && p1_live(u_first, w, FA) && !(V & 16)) issue(u_first);
+    if (lane == 0 && p1_live(u_first, w, FA)) issue(u_first);
 
     // The staged rows of tile u are pulled into registers one step ahead (at the end of the step before the one
     // that consumes them) and the stage goes straight back to TMA for tile u + 1, which then has a whole step to
@@ -146,7 +144,7 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
 #pragma unroll
     for (int q = 0; q < kRawWords; ++q) raw_a[q] = raw_b[q] = 0u;
     auto load_stage = [&](int u) {
-        if (!(V & 16)) mbar_wait(&sm.bar[w], (uint32_t)((u - u_first) & 1));
+        mbar_wait(&sm.bar[w], (uint32_t)((u - u_first) & 1));
         const uint8_t* ra = &sm.raw[w][0][lane * kRawPitch];
         const uint8_t* rb = &sm.raw[w][1][lane * kRawPitch];
         uint32_t dep = 0;
@@ -158,7 +156,7 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
             dep ^= va.x ^ vb.x;
         }
         const unsigned held = __ballot_sync(0xffffffffu, dep != 0x5bd1e995u);
-        if (lane == 0 && held != 0u && p1_live(u + 1, w, FA) && !(V & 16)) issue(u + 1);
+        if (lane == 0 && held != 0u && p1_live(u + 1, w, FA)) issue(u + 1);
     };
     if (sched_u(kTStart, 1, w) == u_first && p1_live(u_first, w, FA)) load_stage(u_first);  // warp 7
 
@@ -194,9 +192,9 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
             }
         }
         // (when P1 is not live the raw registers are stale; its results are never stored)
-        main_step<V>(st, a, raw_a, raw_b, first_a, first_b, lane);
+        main_step(st, a, raw_a, raw_b, first_a, first_b, lane);
         if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1);
-        if (!(V & 8)) cta_barrier();
+        cta_barrier();
     }
 }
 
@@ -218,20 +216,18 @@ int fused2_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64
     int dev = 0, sms = 148;
     VPDQ_CUDA(cudaGetDevice(&dev));
     VPDQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);  // persistent: one CTA per SM
-    static const int variant = [] { const char* e = getenv("VPDQ_B200_FUSED2_VARIANT"); return e ? atoi(e) : 0; }();
-#define VPDQ_LAUNCH_V(VV)                                                                                              \
-    case VV:                                                                                                          \
-        VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_jarosz2<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                       (int)sizeof(Fused2Smem)));                                                     \
-        kx_fused_jarosz2<VV><<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, d_frames, (long long)n_frames, \
-                                                                                  d_a64);                              \
-        break;
-    switch (variant) {
-        VPDQ_LAUNCH_V(0) VPDQ_LAUNCH_V(1) VPDQ_LAUNCH_V(2) VPDQ_LAUNCH_V(4) VPDQ_LAUNCH_V(8) VPDQ_LAUNCH_V(16) VPDQ_LAUNCH_V(32)
-        VPDQ_LAUNCH_V(64) VPDQ_LAUNCH_V(70) VPDQ_LAUNCH_V(71) VPDQ_LAUNCH_V(24) VPDQ_LAUNCH_V(6) VPDQ_LAUNCH_V(17)
-        default: set_error("bad variant"); return VPDQ_B200_ERR_INVALID;
+    static std::mutex mu;
+    static bool attr_done[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_jarosz2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(Fused2Smem)));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
     }
+    const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);  // persistent: one CTA per SM
+    kx_fused_jarosz2<<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, d_frames, (long long)n_frames, d_a64);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

@@ -2,7 +2,7 @@
 // (kx_fused_jarosz2, pdq_fused2.cu): every lane carries the same line of TWO frames in the two halves of a
 // 64-bit register pair, so each running-sum step, each luma product and each shared-memory access is one
 // packed instruction (FADD2 / FFMA2 / FMUL2, LDS.64 / STS.64 / .128) for both frames.  Rounding is per
-// component, IEEE round-to-nearest -- bit-identical to the scalar op order of oracle/pdq_oracle.c.
+// component, IEEE round-to-nearest -- bit-identical to the scalar op order of the CPU oracle.
 //
 // Compiled twice: by nvcc into the kernel and by g++ into the CPU emulator (tests/emu/pdq_fused2_emu.cpp)
 // that executes the very same schedule warp by warp and lane by lane, so every index in here is checked
@@ -214,7 +214,6 @@ VPDQ2_HD void swap_f2(F2& a, F2& b) { const F2 t = a; a = b; b = t; }
 // first_a / first_b: bytes 0..7 of those image rows (pixels 0, 1; used when s1 == 0).
 // (The kernel pulls them into registers at the END of the previous step and hands the staging buffers back to
 // TMA at once, so that the copy for the step after next has a whole step to land.)
-template <int V = 0>
 VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a)[kRawWords],
                         const uint32_t (&raw_b)[kRawWords], const uint32_t (&first_a)[2],
                         const uint32_t (&first_b)[2], int lane) {
@@ -249,7 +248,7 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
 
     VPDQ2_UNROLL
     for (int k = 0; k < kTile; ++k) {
-        if ((k & 3) == 0 && k + 4 < kTile && !(V & 4)) {  // P3's next chunk (columns k+4..k+7): P1 stores there at k+7
+        if ((k & 3) == 0 && k + 4 < kTile) {  // P3's next chunk (columns k+4..k+7): P1 stores there at k+7
             const F4 v0 = *reinterpret_cast<const F4*>(row_a + k + 4), v1 = *reinterpret_cast<const F4*>(row_a + k + 6);
             F2(&dst)[4] = x3[((k >> 2) + 1) & 1];
             dst[0] = v0.lo; dst[1] = v0.hi; dst[2] = v1.lo; dst[3] = v1.hi;
@@ -261,16 +260,15 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
         }
         // P1: luma + row pass 1, fed pixel 32*s1 + 2 + k -> output column 32*s1 + k
         {
-            const F2 v = st.c1.feed((V & 1) ? F2{bits_to_float(raw_a[(kRawSkip + 3 * k) >> 2]), bits_to_float(raw_b[(kRawSkip + 3 * k) >> 2])}
-                                            : luma_pair_at(raw_a, raw_b, kRawSkip + 3 * k));
+            const F2 v = st.c1.feed(luma_pair_at(raw_a, raw_b, kRawSkip + 3 * k));
             y1[k & 3] = edge_scale(v, k, a.s1);
-            if ((k & 3) == 3 && a.live1 && !(V & 64)) {
+            if ((k & 3) == 3 && a.live1) {
                 *reinterpret_cast<F4*>(row_a + k - 3) = F4{y1[0], y1[1]};
                 *reinterpret_cast<F4*>(row_a + k - 1) = F4{y1[2], y1[3]};
             }
         }
         // P2: column pass 1 in place, fed P1 row 32*b2 + 2 + k -> output row 32*b2 + k
-        if (!(V & 2)) {
+        {
             F2 x2 = x2_q[k & 1];
             if (k + 2 < kTile) x2_q[k & 1] = col_b[(k + 2) * kPitch];
             if (k == 30) n0 = x2;
