@@ -1,13 +1,15 @@
 #!/usr/bin/env bash
-# one gpurun call: parity tests, A/B bench lines, ncu launch list + full capture of the dominant kernel
+# one gpurun call: parity tests, A/B bench lines (finalize kernel k5 vs k4), kernel-only timings
 set -u
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
-for impl in fused2 fused; do
-  VPDQ_B200_PDQ_IMPL=$impl timeout 300 python bench.py --steps 10 --warmup 3 --no-hamming --no-luma --no-cpu-baseline > gpurun_out/bench_ab_$impl.json 2> gpurun_out/bench_ab_$impl.err
-  cat gpurun_out/bench_ab_$impl.json
+for fin in k5 k4; do
+  VPDQ_B200_FINALIZE=$fin timeout 300 python bench.py --steps 10 --warmup 3 --no-hamming --no-luma --no-cpu-baseline > gpurun_out/bench_fin_$fin.json 2> gpurun_out/bench_fin_$fin.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_fin_$fin.json"))
+print("$fin", "value", round(d["value"]), "ms/step", round(d["ms_per_step"],4), "kx ms", round(d["roofline"]["kernel_ms_per_launch"],4), "frac", round(d["roofline"]["frac"],4), "e2e", round(d["e2e"]["value"]))
+PY
 done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_fused2.csv python tools/prof_pdq.py fused2 > gpurun_out/prof_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:kx_fused_jarosz2 -s 2 -c 1 -o gpurun_out/prof_fused2 -f python tools/prof_pdq.py fused2 > gpurun_out/prof_full.log 2>&1
-tail -3 gpurun_out/prof_full.log
+python tools/kx_bench.py 4096 10
