@@ -80,8 +80,7 @@ __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" :
 }  // namespace
 
 __global__ void __launch_bounds__(kFused2Threads, 1)
-    kx_fused_jarosz2(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ frames,
-                     long long n_frames_total, float* __restrict__ a64) {
+    kx_fused_jarosz2(const __grid_constant__ CUtensorMap tmap, long long n_frames_total, float* __restrict__ a64) {
     extern __shared__ __align__(128) uint8_t smem_bytes2[];
     Fused2Smem& sm = *reinterpret_cast<Fused2Smem*>(smem_bytes2);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,7 +91,6 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
     if (F == 0) return;
     const int FA = (F + 1) >> 1, FB = F - FA;
     const long long half_a = f_begin, half_b = f_begin + FA;
-    const long long total_rows = n_frames_total * 512;
 
     if (w < kMainWarps && lane == 0) mbar_init(&sm.bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,22 +175,8 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
         a.tile_b = sm.slot[(T - 1) & 1][a.b2 & 7];
         a.t3_w = sm.t3[T & 1] + (a.s3 & 7) * kT3Strip;
 
-        uint32_t first_a[2] = {0u, 0u}, first_b[2] = {0u, 0u};
-        if (a.live1 && a.s1 == 0) {
-            const long long ra = p1_row0(half_a, u1, w) + lane, rb = p1_row0(half_b, u1, w) + lane;
-            if (ra >= 0 && ra < total_rows) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(frames + (size_t)ra * 1536));
-                first_a[0] = v.x;
-                first_a[1] = v.y;
-            }
-            if (rb >= 0 && rb < total_rows) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(frames + (size_t)rb * 1536));
-                first_b[0] = v.x;
-                first_b[1] = v.y;
-            }
-        }
         // (when P1 is not live the raw registers are stale; its results are never stored)
-        main_step(st, a, raw_a, raw_b, first_a, first_b, lane);
+        main_step(st, a, raw_a, raw_b, lane);
         if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1);
         cta_barrier();
     }
@@ -227,7 +211,7 @@ int fused2_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64
         }
     }
     const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);  // persistent: one CTA per SM
-    kx_fused_jarosz2<<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, d_frames, (long long)n_frames, d_a64);
+    kx_fused_jarosz2<<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, (long long)n_frames, d_a64);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

@@ -210,13 +210,13 @@ VPDQ2_HD void swap_chain(Chain2& a, Chain2& b) { const Chain2 t = a; a = b; b = 
 VPDQ2_HD void swap_f2(F2& a, F2& b) { const F2 t = a; a = b; b = t; }
 
 // One lane's work for one step of a main warp: the three roles, interleaved element by element.
-// raw_a / raw_b: the lane's staged RGB rows of the two frames (28 words, pixels from byte kRawSkip);
-// first_a / first_b: bytes 0..7 of those image rows (pixels 0, 1; used when s1 == 0).
+// raw_a / raw_b: the lane's staged RGB rows of the two frames (28 words; the step's 32 pixels start at byte
+// kRawSkip; bytes 0..5 are the two pixels in front of them -- for strip 0 that is pixels 0, 1 of the image row,
+// the prologue of the running sum, so no separate load is needed for them).
 // (The kernel pulls them into registers at the END of the previous step and hands the staging buffers back to
 // TMA at once, so that the copy for the step after next has a whole step to land.)
 VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a)[kRawWords],
-                        const uint32_t (&raw_b)[kRawWords], const uint32_t (&first_a)[2],
-                        const uint32_t (&first_b)[2], int lane) {
+                        const uint32_t (&raw_b)[kRawWords], int lane) {
     // ---- per-role prologues (warp-uniform conditions) ----
     if (a.swap2) {
         swap_chain(st.c2, st.c2_parked);
@@ -225,8 +225,8 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
     }
     if (a.s1 == 0) {  // new row: pixels 0,1 are fed without output
         st.c1.init();
-        st.c1.feed(luma_pair_at(first_a, first_b, 0));
-        st.c1.feed(luma_pair_at(first_a, first_b, 3));
+        st.c1.feed(luma_pair_at(raw_a, raw_b, 0));
+        st.c1.feed(luma_pair_at(raw_a, raw_b, 3));
     }
     if (a.b2 == 0) {  // new column: P1 rows 0,1 were stashed from the previous frame's band 15
         st.c2.init();

@@ -94,20 +94,14 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
                 if (a.live1 && s->regs_hold[w] != u1) ++errors;  // the registers must hold this step's rows
                 const uint8_t (&staged)[2][kRawBoxBytes] = s->regs[w];
                 for (int lane = 0; lane < 32; ++lane) {
-                    uint32_t first_a[2] = {0, 0}, first_b[2] = {0, 0};
                     uint32_t raw_a[kRawWords], raw_b[kRawWords];
                     memset(raw_a, 0, sizeof raw_a);
                     memset(raw_b, 0, sizeof raw_b);
                     if (a.live1) {
-                        if (a.s1 == 0) {
-                            const long long ra = p1_row0(half_a, u1, w) + lane, rb = p1_row0(half_b, u1, w) + lane;
-                            if (ra >= 0 && ra < total_rows) memcpy(first_a, frames + ra * 1536, 8);
-                            if (rb >= 0 && rb < total_rows) memcpy(first_b, frames + rb * 1536, 8);
-                        }
                         memcpy(raw_a, &staged[0][lane * kRawPitch], kRawPitch);
                         memcpy(raw_b, &staged[1][lane * kRawPitch], kRawPitch);
                     }
-                    main_step(s->st[w][lane], a, raw_a, raw_b, first_a, first_b, lane);
+                    main_step(s->st[w][lane], a, raw_a, raw_b, lane);
                 }
                 if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1, w);
             }
