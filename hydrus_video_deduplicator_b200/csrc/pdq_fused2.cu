@@ -56,6 +56,17 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, uint32_t parity) {  // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     // bounded: a mis-programmed copy must not hang the GPU; ~1 s worth of polling, then flag and go on
 #pragma unroll 1
@@ -141,8 +152,8 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
     uint32_t raw_a[kRawWords], raw_b[kRawWords];
 #pragma unroll
     for (int q = 0; q < kRawWords; ++q) raw_a[q] = raw_b[q] = 0u;
-    auto load_stage = [&](int u) {
-        mbar_wait(&sm.bar[w], (uint32_t)((u - u_first) & 1));
+    auto load_stage = [&](int u, bool landed) {
+        if (!landed) mbar_wait(&sm.bar[w], (uint32_t)((u - u_first) & 1));
         const uint8_t* ra = &sm.raw[w][0][lane * kRawPitch];
         const uint8_t* rb = &sm.raw[w][1][lane * kRawPitch];
         uint32_t dep = 0;
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
         const unsigned held = __ballot_sync(0xffffffffu, dep != 0x5bd1e995u);
         if (lane == 0 && held != 0u && p1_live(u + 1, w, FA)) issue(u + 1);
     };
-    if (sched_u(kTStart, 1, w) == u_first && p1_live(u_first, w, FA)) load_stage(u_first);  // warp 7
+    if (sched_u(kTStart, 1, w) == u_first && p1_live(u_first, w, FA)) load_stage(u_first, false);  // warp 7
 
     LaneState st;
     st.init();
@@ -176,8 +187,12 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
         a.t3_w = sm.t3[T & 1] + (a.s3 & 7) * kT3Strip;
 
         // (when P1 is not live the raw registers are stale; its results are never stored)
-        main_step(st, a, raw_a, raw_b, lane);
-        if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1);
+        const bool next_live = p1_live(u1 + 1, w, FA);
+        bool landed = false;  // the next step's boxes, polled late in this step (hides the poll's latency)
+        main_step(st, a, raw_a, raw_b, lane, [&]() {
+            if (next_live) landed = mbar_test_wait(&sm.bar[w], (uint32_t)((u1 + 1 - u_first) & 1));
+        });
+        if (next_live) load_stage(u1 + 1, landed);
         cta_barrier();
     }
 }

@@ -215,8 +215,12 @@ VPDQ2_HD void swap_f2(F2& a, F2& b) { const F2 t = a; a = b; b = t; }
 // the prologue of the running sum, so no separate load is needed for them).
 // (The kernel pulls them into registers at the END of the previous step and hands the staging buffers back to
 // TMA at once, so that the copy for the step after next has a whole step to land.)
+// probe(): called at k == kProbeAt; the kernel polls (without blocking) whether the NEXT step's boxes have landed,
+// so that the poll's latency is hidden behind the rest of the step.
+constexpr int kProbeAt = 26;
+template <typename Probe>
 VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a)[kRawWords],
-                        const uint32_t (&raw_b)[kRawWords], int lane) {
+                        const uint32_t (&raw_b)[kRawWords], int lane, Probe probe) {
     // ---- per-role prologues (warp-uniform conditions) ----
     if (a.swap2) {
         swap_chain(st.c2, st.c2_parked);
@@ -248,6 +252,7 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
 
     VPDQ2_UNROLL
     for (int k = 0; k < kTile; ++k) {
+        if (k == kProbeAt) probe();
         if ((k & 3) == 0 && k + 4 < kTile) {  // P3's next chunk (columns k+4..k+7): P1 stores there at k+7
             const F4 v0 = *reinterpret_cast<const F4*>(row_a + k + 4), v1 = *reinterpret_cast<const F4*>(row_a + k + 6);
             F2(&dst)[4] = x3[((k >> 2) + 1) & 1];

@@ -101,7 +101,7 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
                         memcpy(raw_a, &staged[0][lane * kRawPitch], kRawPitch);
                         memcpy(raw_b, &staged[1][lane * kRawPitch], kRawPitch);
                     }
-                    main_step(s->st[w][lane], a, raw_a, raw_b, lane);
+                    main_step(s->st[w][lane], a, raw_a, raw_b, lane, [] {});
                 }
                 if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1, w);
             }
