@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
     kx_fused_jarosz2(const __grid_constant__ CUtensorMap tmap, long long n_frames_total, float* __restrict__ a64) {
     extern __shared__ __align__(128) uint8_t smem_bytes2[];
     Fused2Smem& sm = *reinterpret_cast<Fused2Smem*>(smem_bytes2);
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the shuffle tells the compiler that w is warp-uniform: index arithmetic and TMA operands go to uniform registers)
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     const long long f_begin = n_frames_total * blockIdx.x / gridDim.x;
     const long long f_end = n_frames_total * (blockIdx.x + 1) / gridDim.x;
