@@ -8,7 +8,7 @@ workload "hash" (default; BASELINE.json configs[1]: "hash 100k synthetic frames"
     a step = one pass of the PDQ frame-hash path over one batch of synthetic 512x512 RGB24 frames.
     value = frames/s with the batch already resident in HBM (CUDA events on the launching stream, max over
             ranks); e2e = the same through the host-pointer C ABI call (pinned host memory -> H2D -> kernels
-            -> D2H inside the timed region).  Each step's input (3.2 GB) is far larger than L2 (126 MB).
+            -> D2H inside the timed region).  Each step's input (6.4 GB) is far larger than L2 (126 MB).
     At N = 1 the JSON line also carries the Hamming figures (streaming scan GB/s vs the HBM peak at
     n_query = 1/2/4/8, and 1M x 1M all-pairs comparisons/s) under "hamming".
 workload "hamming" (BASELINE.json configs[3]): pair-comparisons/s of the all-pairs kernel with the target
@@ -342,7 +342,8 @@ def run_b200(args) -> None:
                     "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
                     "traffic_source": "profiles/r01_traffic.json (ncu --set full dram__bytes_read+write, per frame x "
                                       "frames per launch)",
-                    "note": "issue-bound, not HBM-bound: see DESIGN.md 4.2"}
+                    "note": "bound by the shared-memory pipe (tile hand-over between row and column passes), not by "
+                            "HBM: see DESIGN.md 4.2"}
 
         # ---- end to end through the host-pointer C ABI (pinned host memory) ----
         import ctypes as C
@@ -598,8 +599,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=["hash", "hamming"], default="hash")
-    ap.add_argument("--batch", type=int, default=4096, help="frames per step per GPU (hash workload)")
-    ap.add_argument("--pool-batches", type=int, default=4, help="distinct device batches cycled through")
+    ap.add_argument("--batch", type=int, default=8192, help="frames per step per GPU (hash workload)")
+    ap.add_argument("--pool-batches", type=int, default=3, help="distinct device batches cycled through")
     ap.add_argument("--e2e-batch", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--scan-hashes", type=int, default=10_000_000)
