@@ -52,6 +52,12 @@ def jarosz_kernel_name() -> str:
         os.environ.get("VPDQ_B200_PDQ_IMPL", ""), "kx_fused_jarosz2")
 
 
+def finalize_kernel_name() -> str:
+    if os.environ.get("VPDQ_B200_PDQ_IMPL", "") == "lines":
+        return "k4_colpass_finalize<false>"
+    return "k4_colpass_finalize<true>" if os.environ.get("VPDQ_B200_FINALIZE", "") == "k4" else "k5_finalize"
+
+
 def measured_traffic_per_frame() -> float | None:
     """DRAM bytes per frame of the dominant PDQ kernel from the committed ncu capture (profiles/r01_traffic.json)."""
     p = ROOT / "profiles" / "r01_traffic.json"
@@ -336,7 +342,7 @@ def run_b200(args) -> None:
                     "traffic": (tpf * B) if tpf else None, "peak_source": peak_src,
                     "kernel": jarosz_kernel_name(), "kernel_ms_per_launch": kx_ms,
                     "kernel_share_of_step": kx_ms / ms_per_step,
-                    "pipeline": {"kernels": jarosz_kernel_name() + " + k4_colpass_finalize<true>", "achieved": pipeline_gbs,
+                    "pipeline": {"kernels": jarosz_kernel_name() + " + " + finalize_kernel_name(), "achieved": pipeline_gbs,
                                  "frac": pipeline_gbs / peak},
                     "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_FRAME,
                     "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
