@@ -494,7 +494,7 @@ def cpu_baseline(args, pool0, torch) -> dict:
 
 def luma_section(torch, dev_api, dev, local, args) -> dict:
     """BASELINE's "512x512 luma frames" variant: 8-bit gray input, DEFINED as the RGB frame R=G=B=L (SURVEY.md note
-    a-1; one byte per pixel crosses PCIe instead of three).  Uses the v1 line kernels (csrc/pdq_kernels.cu)."""
+    a-1; one byte per pixel crosses PCIe instead of three).  Same kernels as the RGB24 path (kx_fused_jarosz2<1>)."""
     import ctypes as C
 
     from hydrus_video_deduplicator_b200 import _ffi
@@ -530,7 +530,9 @@ def luma_section(torch, dev_api, dev, local, args) -> dict:
     same = bool(torch.equal(dev_api.hash_frames(rgb)[0], h[:4]) and torch.equal(hh[:4], h[:4].cpu()))
     return {"frames_per_s_device_resident": dev_rate, "frames_per_s_e2e": e2e_rate, "frames": n,
             "bytes_per_frame": 512 * 512, "equals_rgb_expansion": same,
-            "kernels": "k1_luma_rowpass<1> + k2_colpass + k3_rowpass_dec + k4_colpass_finalize<false>"}
+            "kernels": ("k1_luma_rowpass<1> + k2_colpass + k3_rowpass_dec + k4_colpass_finalize<false>"
+                        if os.environ.get("VPDQ_B200_PDQ_IMPL", "") in ("lines", "fused")
+                        else "kx_fused_jarosz2<1> + k5_finalize")}
 
 
 def hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args) -> dict:

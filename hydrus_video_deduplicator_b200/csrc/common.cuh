@@ -42,7 +42,7 @@ size_t fused_scratch_per_frame();
 int fused_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int fused_debug_flags(int* flags);
 // the same, two frames per lane in packed fp32 pairs (pdq_fused2.cu) -- the default
-int fused2_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream);
+int fused2_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int fused2_debug_flags(int* flags);
 // which Jarosz pipeline hashes RGB24 frames: 2 = frame-pair fused kernel (default), 1 = fused (VPDQ_B200_PDQ_IMPL=fused),
 // 0 = v1 line kernels (=lines).  All are CUDA and bit-identical; the switch exists for A/B measurements.

@@ -176,16 +176,17 @@ int fused_debug_flags(int* flags) {
 
 size_t fused_scratch_per_frame() { return (size_t)64 * 64 * sizeof(float); }
 
-// tensor map over the whole batch seen as [n*512 rows][1536 B], box = 32 rows x 112 B (shared with pdq_fused2.cu)
-int fused_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, CUtensorMap* tmap) {
+// tensor map over the whole batch seen as [n*512 rows][512*channels B], box = 32 rows x 112 B (RGB24) or 48 B (gray)
+// (shared with pdq_fused2.cu)
+int fused_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, int channels, CUtensorMap* tmap) {
     EncodeTiledFn encode = get_encode();
     if (!encode) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return VPDQ_B200_ERR_CUDA;
     }
-    const cuuint64_t gdim[2] = {1536, (cuuint64_t)n_frames * 512};
-    const cuuint64_t gstride[1] = {1536};
-    const cuuint32_t box[2] = {(cuuint32_t)kRawPitch, (cuuint32_t)kTile};
+    const cuuint64_t gdim[2] = {(cuuint64_t)512 * channels, (cuuint64_t)n_frames * 512};
+    const cuuint64_t gstride[1] = {(cuuint64_t)512 * channels};
+    const cuuint32_t box[2] = {(cuuint32_t)(channels == 3 ? kRawPitch : 48), (cuuint32_t)kTile};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(d_frames), gdim, gstride, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -200,7 +201,7 @@ int fused_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, CUtensorMap
 // RGB24 frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane
 int fused_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream) {
     CUtensorMap tmap;
-    const int rc_map = fused_make_tensor_map(d_frames, n_frames, &tmap);
+    const int rc_map = fused_make_tensor_map(d_frames, n_frames, 3, &tmap);
     if (rc_map) return rc_map;
     int dev = 0, sms = 148;
     VPDQ_CUDA(cudaGetDevice(&dev));

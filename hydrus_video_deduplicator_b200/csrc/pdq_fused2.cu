@@ -23,12 +23,12 @@
 namespace vpdq {
 using namespace vpdq_core2;
 
-int fused_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, CUtensorMap* tmap);  // pdq_fused.cu
+int fused_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, int channels, CUtensorMap* tmap);  // pdq_fused.cu
 
 constexpr int kFused2Threads = 32 * kWarps;  // 288
 
 struct Fused2Smem {
-    alignas(128) uint8_t raw[kMainWarps][2][kRawBoxBytes];  //  57 344 B  TMA destinations (one stage per warp, 2 frames)
+    alignas(128) uint8_t raw[kMainWarps][2][kRawBoxBytesMax];  //  57 344 B  TMA destinations (one stage per warp, 2 frames)
     alignas(16) F2 slot[2][kMainWarps][kSlotF2];             // 139 264 B  tile hand-over, by step parity
     alignas(16) F2 t3[2][kMainWarps * kT3Strip];             //  18 432 B  P3 -> P4 hand-over, by step parity
     alignas(8) unsigned long long bar[kMainWarps];           //      64 B  mbarriers
@@ -90,6 +90,7 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, %0;" ::"n"(kFused2Threads) : "memory"); }
 }  // namespace
 
+template <int CH>  // 3: RGB24 frames, 1: 8-bit gray frames (== R = G = B)
 __global__ void __launch_bounds__(kFused2Threads, 1)
     kx_fused_jarosz2(const __grid_constant__ CUtensorMap tmap, long long n_frames_total, float* __restrict__ a64) {
     extern __shared__ __align__(128) uint8_t smem_bytes2[];
@@ -137,10 +138,11 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
 
     // ---------------- main warps ----------------
     const int u_first = p1_first(w);
-    auto issue = [&](int u) {  // lane 0: stage the raw RGB boxes (both frames) of P1 tile u of this warp
-        mbar_expect_tx(&sm.bar[w], 2 * kRawBoxBytes);
-        tma_load_2d(&sm.raw[w][0][0], &tmap, p1_box_x(u), (int)p1_row0(half_a, u, w), &sm.bar[w]);
-        tma_load_2d(&sm.raw[w][1][0], &tmap, p1_box_x(u), (int)p1_row0(half_b, u, w), &sm.bar[w]);
+    constexpr int kRawPitch = Raw<CH>::kPitch, kRawWords = Raw<CH>::kWords;
+    auto issue = [&](int u) {  // lane 0: stage the raw boxes (both frames) of P1 tile u of this warp
+        mbar_expect_tx(&sm.bar[w], 2 * Raw<CH>::kBoxBytes);
+        tma_load_2d(&sm.raw[w][0][0], &tmap, p1_box_x<CH>(u), (int)p1_row0(half_a, u, w), &sm.bar[w]);
+        tma_load_2d(&sm.raw[w][1][0], &tmap, p1_box_x<CH>(u), (int)p1_row0(half_b, u, w), &sm.bar[w]);
     };
     if (lane == 0 && p1_live(u_first, w, FA)) issue(u_first);
 
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kFused2Threads, 1)
         // (when P1 is not live the raw registers are stale; its results are never stored)
         const bool next_live = p1_live(u1 + 1, w, FA);
         bool landed = false;  // the next step's boxes, polled late in this step (hides the poll's latency)
-        main_step(st, a, raw_a, raw_b, lane, [&]() {
+        main_step<CH>(st, a, raw_a, raw_b, lane, [&]() {
             if (next_live) landed = mbar_test_wait(&sm.bar[w], (uint32_t)((u1 + 1 - u_first) & 1));
         });
         if (next_live) load_stage(u1 + 1, landed);
@@ -208,10 +210,10 @@ int fused2_debug_flags(int* flags) {
     return VPDQ_B200_OK;
 }
 
-// RGB24 frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane
-int fused2_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream) {
+// RGB24 (channels = 3) or 8-bit gray (channels = 1) frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane
+int fused2_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream) {
     CUtensorMap tmap;
-    int rc = fused_make_tensor_map(d_frames, n_frames, &tmap);
+    int rc = fused_make_tensor_map(d_frames, n_frames, channels, &tmap);
     if (rc) return rc;
     int dev = 0, sms = 148;
     VPDQ_CUDA(cudaGetDevice(&dev));
@@ -221,13 +223,18 @@ int fused2_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64
     {
         std::lock_guard<std::mutex> lk(mu);
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_jarosz2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_jarosz2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(Fused2Smem)));
+            VPDQ_CUDA(cudaFuncSetAttribute(kx_fused_jarosz2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(Fused2Smem)));
             if (dev >= 0 && dev < 64) attr_done[dev] = true;
         }
     }
     const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);  // persistent: one CTA per SM
-    kx_fused_jarosz2<<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, (long long)n_frames, d_a64);
+    if (channels == 3)
+        kx_fused_jarosz2<3><<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, (long long)n_frames, d_a64);
+    else
+        kx_fused_jarosz2<1><<<grid, kFused2Threads, sizeof(Fused2Smem), stream>>>(tmap, (long long)n_frames, d_a64);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

@@ -113,10 +113,18 @@ VPDQ2_HD F2 div3(F2 v) {
 constexpr int kMainWarps = 8;
 constexpr int kWarps = kMainWarps + 1;            // + the P4 warp
 constexpr int kTile = 32;
-constexpr int kRawPitch = 112;                    // bytes per staged row (7 x 16): bytes 6..101 used
-constexpr int kRawWords = kRawPitch / 4;          // 28
-constexpr int kRawSkip = 6;                       // first used byte of a staged row
-constexpr int kRawBoxBytes = kRawPitch * kTile;   // 3584 B per warp per frame
+// staged raw rows, by channel count CH (3: RGB24, 1: 8-bit gray == R = G = B): a step's 32 pixels plus the two
+// in front of them, rounded up to the 16-byte granularity of a TMA box
+template <int CH>
+struct Raw {
+    static constexpr int kPitch = CH == 3 ? 112 : 48;    // bytes per staged row: bytes 2*CH .. 34*CH - 1 used; at both
+                                                          // pitches the lane = row 128-bit reads are bank-conflict free
+    static constexpr int kWords = kPitch / 4;            // 28 / 12
+    static constexpr int kSkip = 2 * CH;                 // first byte of the step's 32 pixels in a staged row
+    static constexpr int kBoxBytes = kPitch * 32;        // 3584 / 1536 B per warp per frame
+    static constexpr int kStripBytes = 32 * CH;          // 16-byte aligned box start of strip s: kStripBytes * s
+};
+constexpr int kRawBoxBytesMax = Raw<3>::kBoxBytes;
 constexpr int kPitch = kTile + 2;                 // F2 per tile row (272 B = 17 x 16 B): lane=row 128-bit and
                                                   // lane=column 64-bit accesses are both bank-conflict free
 constexpr int kSlotF2 = kTile * kPitch;           // 1088 F2 = 8704 B per tile slot
@@ -148,16 +156,17 @@ VPDQ2_HD F2 edge_scale(F2 v, int k, int t) {
     return v;
 }
 
-// luma of the pixel whose R byte sits at byte offset b0 of the two frames' little-endian word arrays.
+// luma of the pixel whose first byte sits at byte offset b0 of the two frames' little-endian word arrays.
 // u8 -> fp32 product without an I2F: the byte is spliced into the mantissa of 2^23 (PRMT): M = 2^23 + b exactly;
-// fma(c, M, -c*2^23) = RN(c*b), bit-identical to __fmul_rn(c, (float)b)  (c*2^23 is exact)
-template <int N>
+// fma(c, M, -c*2^23) = RN(c*b), bit-identical to __fmul_rn(c, (float)b)  (c*2^23 is exact).
+// CH == 1: gray == R = G = B, the same three-term expression on one byte (SURVEY.md 8 note a-1).
+template <int CH, int N>
 VPDQ2_HD F2 luma_pair_at(const uint32_t (&wa)[N], const uint32_t (&wb)[N], int b0) {
     const float cr = 0.299f, cg = 0.587f, cb = 0.114f, two23 = 8388608.0f;
-    const int b1 = b0 + 1, b2 = b0 + 2;
+    const int b1 = CH == 3 ? b0 + 1 : b0, b2 = CH == 3 ? b0 + 2 : b0;
     const F2 mr{bits_to_float(byte_splice(wa[b0 >> 2], b0 & 3)), bits_to_float(byte_splice(wb[b0 >> 2], b0 & 3))};
-    const F2 mg{bits_to_float(byte_splice(wa[b1 >> 2], b1 & 3)), bits_to_float(byte_splice(wb[b1 >> 2], b1 & 3))};
-    const F2 mb{bits_to_float(byte_splice(wa[b2 >> 2], b2 & 3)), bits_to_float(byte_splice(wb[b2 >> 2], b2 & 3))};
+    const F2 mg = CH == 3 ? F2{bits_to_float(byte_splice(wa[b1 >> 2], b1 & 3)), bits_to_float(byte_splice(wb[b1 >> 2], b1 & 3))} : mr;
+    const F2 mb = CH == 3 ? F2{bits_to_float(byte_splice(wa[b2 >> 2], b2 & 3)), bits_to_float(byte_splice(wb[b2 >> 2], b2 & 3))} : mr;
     const F2 r = f2_fma(f2_splat(cr), mr, f2_splat(-(cr * two23)));
     const F2 g = f2_fma(f2_splat(cg), mg, f2_splat(-(cg * two23)));
     const F2 b = f2_fma(f2_splat(cb), mb, f2_splat(-(cb * two23)));
@@ -187,7 +196,8 @@ VPDQ2_HD int p1_first(int w) { return w == 7 ? -16 : 0; }
 VPDQ2_HD long long p1_row0(long long half_begin, int u, int w) {
     return (half_begin + u_pair(u)) * 512 + 32 * row_band(u, w) + 2;
 }
-VPDQ2_HD int p1_box_x(int u) { return 96 * row_strip(u); }  // 16-byte aligned; pixel 32*strip + 2 is at byte 6
+template <int CH>
+VPDQ2_HD int p1_box_x(int u) { return Raw<CH>::kStripBytes * row_strip(u); }  // 16-byte aligned; pixel 32*strip + 2 is at byte kSkip
 
 struct LaneState {
     Chain2 c1, c2, c2_parked, c3;
@@ -210,17 +220,17 @@ VPDQ2_HD void swap_chain(Chain2& a, Chain2& b) { const Chain2 t = a; a = b; b = 
 VPDQ2_HD void swap_f2(F2& a, F2& b) { const F2 t = a; a = b; b = t; }
 
 // One lane's work for one step of a main warp: the three roles, interleaved element by element.
-// raw_a / raw_b: the lane's staged RGB rows of the two frames (28 words; the step's 32 pixels start at byte
-// kRawSkip; bytes 0..5 are the two pixels in front of them -- for strip 0 that is pixels 0, 1 of the image row,
+// raw_a / raw_b: the lane's staged rows of the two frames (Raw<CH>::kWords words; the step's 32 pixels start at
+// byte kSkip; the bytes in front are the two previous pixels -- for strip 0 that is pixels 0, 1 of the image row,
 // the prologue of the running sum, so no separate load is needed for them).
 // (The kernel pulls them into registers at the END of the previous step and hands the staging buffers back to
 // TMA at once, so that the copy for the step after next has a whole step to land.)
 // probe(): called at k == kProbeAt; the kernel polls (without blocking) whether the NEXT step's boxes have landed,
 // so that the poll's latency is hidden behind the rest of the step.
 constexpr int kProbeAt = 26;
-template <typename Probe>
-VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a)[kRawWords],
-                        const uint32_t (&raw_b)[kRawWords], int lane, Probe probe) {
+template <int CH, typename Probe>
+VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a)[Raw<CH>::kWords],
+                        const uint32_t (&raw_b)[Raw<CH>::kWords], int lane, Probe probe) {
     // ---- per-role prologues (warp-uniform conditions) ----
     if (a.swap2) {
         swap_chain(st.c2, st.c2_parked);
@@ -229,8 +239,8 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
     }
     if (a.s1 == 0) {  // new row: pixels 0,1 are fed without output
         st.c1.init();
-        st.c1.feed(luma_pair_at(raw_a, raw_b, 0));
-        st.c1.feed(luma_pair_at(raw_a, raw_b, 3));
+        st.c1.feed(luma_pair_at<CH>(raw_a, raw_b, 0));
+        st.c1.feed(luma_pair_at<CH>(raw_a, raw_b, CH));
     }
     if (a.b2 == 0) {  // new column: P1 rows 0,1 were stashed from the previous frame's band 15
         st.c2.init();
@@ -265,7 +275,7 @@ VPDQ2_HD void main_step(LaneState& st, const StepArgs& a, const uint32_t (&raw_a
         }
         // P1: luma + row pass 1, fed pixel 32*s1 + 2 + k -> output column 32*s1 + k
         {
-            const F2 v = st.c1.feed(luma_pair_at(raw_a, raw_b, kRawSkip + 3 * k));
+            const F2 v = st.c1.feed(luma_pair_at<CH>(raw_a, raw_b, Raw<CH>::kSkip + CH * k));
             y1[k & 3] = edge_scale(v, k, a.s1);
             if ((k & 3) == 3 && a.live1) {
                 *reinterpret_cast<F4*>(row_a + k - 3) = F4{y1[0], y1[1]};

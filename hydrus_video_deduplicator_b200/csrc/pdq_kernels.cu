@@ -505,7 +505,8 @@ int pdq_set_impl(int impl) {
 int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t* d_hashes, int32_t* d_quality,
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (n_frames == 0) return VPDQ_B200_OK;
-    const int impl = channels == 3 ? pdq_impl() : 0;
+    // gray frames: the frame-pair fused kernel too (the one-frame fused kernel is RGB24 only -> line kernels)
+    const int impl = (channels == 3 || pdq_impl() == 2) ? pdq_impl() : 0;
     const bool fused = impl != 0;
     const size_t per_frame = fused ? fused_scratch_per_frame() : kScratchPerFrame;
     int64_t chunk = (int64_t)(scratch_bytes / per_frame);
@@ -527,7 +528,7 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
         float* bdbg = d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr;
         if (fused) {
             float* a64 = static_cast<float*>(d_scratch);
-            rc = impl == 2 ? fused2_jarosz_launch(src, nf, a64, stream) : fused_jarosz_launch(src, nf, a64, stream);
+            rc = impl == 2 ? fused2_jarosz_launch(src, channels, nf, a64, stream) : fused_jarosz_launch(src, nf, a64, stream);
             if (rc) return rc;
             static const bool use_k4 = [] {  // A/B switch: the previous finalize kernel
                 const char* e = getenv("VPDQ_B200_FINALIZE");

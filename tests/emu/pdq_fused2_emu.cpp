@@ -16,25 +16,27 @@ struct Cta {
     P4State p4[32];
     alignas(16) F2 slot[2][kMainWarps][kSlotF2];
     alignas(16) F2 t3[2][kMainWarps * kT3Strip];
-    uint8_t raw[kMainWarps][2][kRawBoxBytes];
+    uint8_t raw[kMainWarps][2][kRawBoxBytesMax];
     int raw_holds[kMainWarps];  // which tile index u is staged (checks the ring protocol)
-    uint8_t regs[kMainWarps][2][kRawBoxBytes];  // the staged rows as held in the lanes' registers
+    uint8_t regs[kMainWarps][2][kRawBoxBytesMax];  // the staged rows as held in the lanes' registers
     int regs_hold[kMainWarps];
 };
 
+template <int CH>
 void tma_box(const uint8_t* frames, long long total_rows, int x, long long y, uint8_t* dst) {
+    constexpr int kRawPitch = Raw<CH>::kPitch, kRowBytes = 512 * CH;
     for (int r = 0; r < kTile; ++r)
         for (int b = 0; b < kRawPitch; ++b) {
             const long long row = y + r;
             const int col = x + b;
             dst[r * kRawPitch + b] =
-                (row >= 0 && row < total_rows && col >= 0 && col < 1536) ? frames[row * 1536 + col] : 0;
+                (row >= 0 && row < total_rows && col >= 0 && col < kRowBytes) ? frames[row * kRowBytes + col] : 0;
         }
 }
-}  // namespace
 
-extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8_t* frames, long long n_frames, int grid,
-                                                                     float* a64) {
+template <int CH>
+int emu_run(const uint8_t* frames, long long n_frames, int grid, float* a64) {
+    constexpr int kRawPitch = Raw<CH>::kPitch, kRawWords = Raw<CH>::kWords;
     const long long total_rows = n_frames * 512;
     int errors = 0;
     for (int cta = 0; cta < grid; ++cta) {
@@ -58,8 +60,8 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
         }
         for (int l = 0; l < 32; ++l) s->p4[l].init();
         auto issue = [&](int u, int w) {
-            tma_box(frames, total_rows, p1_box_x(u), p1_row0(half_a, u, w), &s->raw[w][0][0]);
-            tma_box(frames, total_rows, p1_box_x(u), p1_row0(half_b, u, w), &s->raw[w][1][0]);
+            tma_box<CH>(frames, total_rows, p1_box_x<CH>(u), p1_row0(half_a, u, w), &s->raw[w][0][0]);
+            tma_box<CH>(frames, total_rows, p1_box_x<CH>(u), p1_row0(half_b, u, w), &s->raw[w][1][0]);
             s->raw_holds[w] = u;
         };
         // pull the staged rows of tile u into "registers" one step ahead, then hand the stage back for tile u + 1
@@ -92,7 +94,7 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
                 if (a.live2) { if (b_touched[a.b2 & 7]) ++errors; b_touched[a.b2 & 7] = true; }
                 if (a.live3) { if (t3_touched[a.s3 & 7]) ++errors; t3_touched[a.s3 & 7] = true; }
                 if (a.live1 && s->regs_hold[w] != u1) ++errors;  // the registers must hold this step's rows
-                const uint8_t (&staged)[2][kRawBoxBytes] = s->regs[w];
+                const uint8_t (&staged)[2][kRawBoxBytesMax] = s->regs[w];
                 for (int lane = 0; lane < 32; ++lane) {
                     uint32_t raw_a[kRawWords], raw_b[kRawWords];
                     memset(raw_a, 0, sizeof raw_a);
@@ -101,7 +103,7 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
                         memcpy(raw_a, &staged[0][lane * kRawPitch], kRawPitch);
                         memcpy(raw_b, &staged[1][lane * kRawPitch], kRawPitch);
                     }
-                    main_step(s->st[w][lane], a, raw_a, raw_b, lane, [] {});
+                    main_step<CH>(s->st[w][lane], a, raw_a, raw_b, lane, [] {});
                 }
                 if (p1_live(u1 + 1, w, FA)) load_stage(u1 + 1, w);
             }
@@ -125,4 +127,11 @@ extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8
         free(s);
     }
     return errors;
+}
+}  // namespace
+
+// channels = 3: frames [n][512][512][3] RGB24; channels = 1: [n][512][512] 8-bit gray
+extern "C" __attribute__((visibility("default"))) int emu_fused2_a64(const uint8_t* frames, long long n_frames, int grid,
+                                                                     float* a64, int channels) {
+    return channels == 3 ? emu_run<3>(frames, n_frames, grid, a64) : emu_run<1>(frames, n_frames, grid, a64);
 }

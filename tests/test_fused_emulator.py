@@ -45,21 +45,25 @@ def emu2():
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so),
                     str(EMU_DIR / "pdq_fused2_emu.cpp")], check=True)
     lib = C.CDLL(str(so))
-    lib.emu_fused2_a64.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    lib.emu_fused2_a64.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
     return lib
 
 
-@pytest.mark.parametrize("n_frames,grid", [(1, 1), (2, 1), (3, 1), (6, 1), (5, 2), (4, 7), (9, 2)])
-def test_emulated_pair_schedule_is_bit_exact(emu2, n_frames, grid):
+@pytest.mark.parametrize("n_frames,grid,channels", [(1, 1, 3), (2, 1, 3), (3, 1, 3), (6, 1, 3), (5, 2, 3), (4, 7, 3),
+                                                   (9, 2, 3), (1, 1, 1), (5, 2, 1), (6, 1, 1)])
+def test_emulated_pair_schedule_is_bit_exact(emu2, n_frames, grid, channels):
     """kx_fused_jarosz2 (two frames per lane, 8 main warps + the P4 warp, deferred power-of-two scaling): odd and
-    even frame counts per CTA (half B one frame shorter), a single frame (half B empty), empty CTAs."""
-    frames = synth.synth_frames(n_frames, seed=57 + n_frames)
+    even frame counts per CTA (half B one frame shorter), a single frame (half B empty), empty CTAs; RGB24 and
+    8-bit gray input."""
+    frames = synth.synth_frames(n_frames, seed=57 + n_frames, channels=channels)
     a64 = np.full((n_frames, 64, 64), np.nan, np.float32)
-    errors = emu2.emu_fused2_a64(frames.ctypes.data_as(C.c_void_p), n_frames, grid, a64.ctypes.data_as(C.c_void_p))
+    errors = emu2.emu_fused2_a64(frames.ctypes.data_as(C.c_void_p), n_frames, grid, a64.ctypes.data_as(C.c_void_p),
+                                 channels)
     assert errors == 0
     assert not np.isnan(a64).any(), "some decimated outputs were never written (or were fed poison)"
     for f in range(n_frames):
-        _, _, a_ref, _ = oracle.pdq_stages(frames[f])
+        rgb = frames[f] if channels == 3 else np.repeat(frames[f][..., None], 3, axis=2)  # gray == R = G = B
+        _, _, a_ref, _ = oracle.pdq_stages(rgb)
         assert a64[f].tobytes() == a_ref.tobytes(), f"frame {f}: decimated plane differs from the oracle"
 
 

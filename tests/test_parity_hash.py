@@ -221,16 +221,20 @@ def test_fused_kernel_is_deterministic_under_load(torch_dev):
     assert _ffi.debug_flags(0) == 0  # no TMA wait ever timed out
 
 
-@pytest.mark.parametrize("n_frames", [1, 2, 3, 147, 149, 297, 1000])
-def test_three_cuda_pipelines_agree(torch_dev, n_frames):
+@pytest.mark.parametrize("n_frames,channels", [(1, 3), (2, 3), (3, 3), (147, 3), (149, 3), (297, 3), (1000, 3),
+                                               (1, 1), (150, 1), (601, 1)])
+def test_three_cuda_pipelines_agree(torch_dev, n_frames, channels):
     """kx_fused_jarosz2 (frame pairs, default), kx_fused_jarosz and the v1 line kernels give identical decimated
-    planes, hashes and quality -- for frame counts that leave CTAs with 0, 1, odd and even numbers of frames --
-    and the default equals the oracle on a strided sample."""
+    planes, hashes and quality -- for frame counts that leave CTAs with 0, 1, odd and even numbers of frames, RGB24
+    and 8-bit gray input (gray: the one-frame fused kernel is RGB-only and falls back to the line kernels) -- and
+    the default equals the oracle on a strided sample."""
     torch, dev = torch_dev
     from bench import device_frames
     from hydrus_video_deduplicator_b200 import _ffi, device
 
     frames = device_frames(torch, n_frames, dev, seed=900 + n_frames)
+    if channels == 1:
+        frames = frames[..., 1].contiguous()
     out = {}
     try:
         for impl in ("fused2", "fused", "lines"):
