@@ -47,6 +47,8 @@ def test_product_does_not_import_the_oracle():
         src = py.read_text()
         assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), py
     for cu in (pkg / "csrc").glob("*"):
+        if not cu.is_file():
+            continue
         assert "oracle/" not in cu.read_text().replace("the oracle", ""), cu
 
 
