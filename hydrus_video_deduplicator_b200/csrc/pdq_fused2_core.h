@@ -35,10 +35,11 @@
 // 4*div3(s), 2*s.  This removes one multiply per element per pass from the inner loop.
 //
 // The 2-sample lag of the box filter (feeding x[r] yields the output for index r-2) is absorbed by shifting
-// what is FED, as in pdq_fused_core.h: P1 is fed pixels 32s+2.. (TMA box at byte 96s, pixels from byte 6;
-// pixels 0,1 = a per-row prologue; pixels 512,513 = TMA out-of-bounds zeros = the drain steps) and its bands
-// hold image rows 32b+2..32b+33, rows 512,513 of a frame being rows 0,1 of the next frame of the same half,
-// which P2 stashes as that frame's prologue while feeding zeros to the current one.
+// what is FED, as in pdq_fused_core.h: P1 is fed pixels 32s+2.. (RGB24: TMA box at byte 96s, pixels from byte 6;
+// gray: box at byte 32s, pixels from byte 2; pixels 0,1 = the bytes in front of them in strip 0's box = the
+// per-row prologue; pixels 512,513 = TMA out-of-bounds zeros = the drain steps) and its bands hold image rows
+// 32b+2..32b+33, rows 512,513 of a frame being rows 0,1 of the next frame of the same half, which P2 stashes as
+// that frame's prologue while feeding zeros to the current one.
 #pragma once
 #include <stdint.h>
 #include <string.h>
