@@ -328,9 +328,8 @@ __global__ void __launch_bounds__(256) k5_finalize(const float* __restrict__ a64
 
 #pragma unroll
     for (int e = t; e < 16 * 64; e += 256) {
-        const float v = __ldg(g_dct + e);
-        Dt[e & 63][e >> 6] = v;
-        Dj[e >> 6][e & 63] = v;
+        Dj[e >> 6][e & 63] = __ldg(g_dct + e);
+        Dt[e >> 4][e & 15] = __ldg(g_dct + (e & 15) * 64 + (e >> 4));  // consecutive lanes -> consecutive words of Dt
     }
     if (t == 0) {
         g_sum = 0u;
