@@ -91,6 +91,17 @@ def test_tree_built_with_injected_distances_obeys_the_reference_invariants():
         assert q in found and found[q] == 1  # a stored hash finds itself (100 % match -> distance 1)
 
 
+@pytest.mark.parametrize("n_videos,frames_per_video,seed", [(2, 3, 1), (3, 0, 2), (41, 0, 3), (97, 2, 4)])
+def test_ragged_and_empty_hashes(n_videos, frames_per_video, seed):
+    """Videos of 0..11 frames (frames_per_video = 0 draws ragged lengths, some empty: an empty hash is similar to
+    nothing, distance 101, DedupeDB.py:555-557), tiny tables, duplicates collapsing onto one phash row."""
+    con = make_db(n_videos=n_videos, frames_per_video=frames_per_video, seed=seed)
+    phashes = [bytes(r[0]) for r in con.execute("SELECT phash FROM shape_perceptual_hashes ORDER BY phash_id")]
+    n = vptree_writer.regenerate_tree(con, distance_fn=oracle_distance_fn(phashes), rng=random.Random(seed))
+    assert n == len(phashes)
+    check_invariants(con)
+
+
 def test_degenerate_tables():
     con = sqlite3.connect(":memory:")
     for stmt in SCHEMA + VPTREE_SCHEMA:
