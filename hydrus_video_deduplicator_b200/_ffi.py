@@ -118,7 +118,7 @@ def kernel_launches() -> int:
     return int(n.value)
 
 
-PDQ_IMPLS = {"lines": 0, "fused": 1, "fused2": 2}
+PDQ_IMPLS = {"lines": 0, "fused": 1, "fused2": 2, "systolic": 3}
 
 
 def set_pdq_impl(name: str) -> None:

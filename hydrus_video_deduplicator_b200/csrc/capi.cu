@@ -156,12 +156,14 @@ int vpdq_b200_debug_flags(int device, int* flags) {
     DeviceGuard g(device);
     if (g.rc) return g.rc;
     VPDQ_CUDA(cudaDeviceSynchronize());
-    int f1 = 0, f2 = 0;
+    int f1 = 0, f2 = 0, f3 = 0;
     int rc = fused_debug_flags(&f1);
     if (rc) return rc;
     rc = fused2_debug_flags(&f2);
     if (rc) return rc;
-    *flags = f1 | f2;
+    rc = systolic_debug_flags(&f3);
+    if (rc) return rc;
+    *flags = f1 | f2 | f3;
     return VPDQ_B200_OK;
 }
 
@@ -314,8 +316,9 @@ int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int widt
         set_error("pdq_jarosz: NULL output or pointers not 16-byte aligned");
         return VPDQ_B200_ERR_INVALID;
     }
-    return pdq_impl() == 1 ? fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream)
-                           : fused2_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream);
+    return pdq_impl() == 1   ? fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream)
+           : pdq_impl() == 3 ? systolic_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream)
+                             : fused2_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream);
 }
 
 int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width, uint8_t* d_dst,

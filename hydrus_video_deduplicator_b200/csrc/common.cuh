@@ -44,7 +44,12 @@ int fused_debug_flags(int* flags);
 // the same, two frames per lane in packed fp32 pairs (pdq_fused2.cu) -- the default
 int fused2_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int fused2_debug_flags(int* flags);
-// which Jarosz pipeline hashes RGB24 frames: 2 = frame-pair fused kernel (default), 1 = fused (VPDQ_B200_PDQ_IMPL=fused),
+// the warp-per-frame systolic kernel (pdq_systolic.cu): no shared-memory transposition between the passes
+int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream);
+int systolic_debug_flags(int* flags);
+int systolic_debug_force_timeout(int value);
+int systolic_timeout_flag_async(int* h_flag, cudaStream_t stream);
+// which Jarosz pipeline hashes RGB24 frames: 3 = systolic, 2 = frame-pair fused kernel (default), 1 = fused (VPDQ_B200_PDQ_IMPL=fused),
 // 0 = v1 line kernels (=lines).  All are CUDA and bit-identical; the switch exists for A/B measurements.
 int pdq_impl();
 int pdq_set_impl(int impl);

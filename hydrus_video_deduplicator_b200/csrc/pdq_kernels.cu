@@ -486,15 +486,15 @@ int pdq_impl() {
     int v = g_pdq_impl.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("VPDQ_B200_PDQ_IMPL");
-        v = (e && strcmp(e, "lines") == 0) ? 0 : (e && strcmp(e, "fused") == 0) ? 1 : 2;
+        v = (e && strcmp(e, "lines") == 0) ? 0 : (e && strcmp(e, "fused") == 0) ? 1 : (e && strcmp(e, "systolic") == 0) ? 3 : 2;
         g_pdq_impl.store(v, std::memory_order_relaxed);
     }
     return v;
 }
 
 int pdq_set_impl(int impl) {
-    if (impl < 0 || impl > 2) {
-        set_error("set_pdq_impl: %d is not one of 0 (lines), 1 (fused), 2 (fused2)", impl);
+    if (impl < 0 || impl > 3) {
+        set_error("set_pdq_impl: %d is not one of 0 (lines), 1 (fused), 2 (fused2), 3 (systolic)", impl);
         return VPDQ_B200_ERR_INVALID;
     }
     g_pdq_impl.store(impl, std::memory_order_relaxed);
@@ -505,7 +505,7 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (n_frames == 0) return VPDQ_B200_OK;
     // gray frames: the frame-pair fused kernel too (the one-frame fused kernel is RGB24 only -> line kernels)
-    const int impl = (channels == 3 || pdq_impl() == 2) ? pdq_impl() : 0;
+    const int impl = (channels == 3 || pdq_impl() >= 2) ? pdq_impl() : 0;
     const bool fused = impl != 0;
     const size_t per_frame = fused ? fused_scratch_per_frame() : kScratchPerFrame;
     int64_t chunk = (int64_t)(scratch_bytes / per_frame);
@@ -527,7 +527,9 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
         float* bdbg = d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr;
         if (fused) {
             float* a64 = static_cast<float*>(d_scratch);
-            rc = impl == 2 ? fused2_jarosz_launch(src, channels, nf, a64, stream) : fused_jarosz_launch(src, nf, a64, stream);
+            rc = impl == 3   ? systolic_jarosz_launch(src, channels, nf, a64, stream)
+                 : impl == 2 ? fused2_jarosz_launch(src, channels, nf, a64, stream)
+                             : fused_jarosz_launch(src, nf, a64, stream);
             if (rc) return rc;
             static const bool use_k4 = [] {  // A/B switch: the previous finalize kernel
                 const char* e = getenv("VPDQ_B200_FINALIZE");
