@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(kSysThreads, 1)
 
     LaneState L;
     L.init(lane);
-    // stream position of lane 0 in the NEXT step (lane 31 prepares that row's prologue)
-    int f0n = -1, r0n = kStepsPerFrame + kFirstStep + 1;
+    // stream position of lane 0 TWO steps ahead (lane 31 prepares that row's prologue pixels one luma stage early)
+    int f0n = -1, r0n = kStepsPerFrame + kFirstStep + 2;
 
     for (int E = 0; E < first_loop_event(); ++E) issue(E);
     int issued = first_loop_event() - 1, waited = -1;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
 
     auto step = [&](int t, auto jtag) {
         constexpr int J = decltype(jtag)::value;
-        if (J == 3) {
+        if (J == kEventPhase) {
             const int Ew = (t + kWaitLead) >> 2, Ei = (t + kIssueLead) >> 2;
             if (Ew >= 0) {
                 wait(Ew);
@@ -159,14 +159,13 @@ __global__ void __launch_bounds__(kSysThreads, 1)
             issue(Ei);
             issued = Ei;
         }
+        // the raw window of the NEXT step's row (its lumas are this step's filler work)
         uint32_t w[R::kWords];
         {
-            const uint32_t off = L.reads_image(F) ? lane_base + ((t - lane) & (kRing - 1)) * R::kSegPitch : zeros;
-            uint32_t last = off + 16 * (R::kChunks - 1);
-            if (lane == 31) {
-                const bool nimg = (unsigned)f0n < (unsigned)F && r0n < kImageRows;
-                last = nimg ? ring + ((t + 1) & (kRing - 1)) * R::kSegPitch : zeros;
-            }
+            const uint32_t off = L.next_reads_image(F) ? lane_base + ((t + 1 - lane) & (kRing - 1)) * R::kSegPitch : zeros;
+            const bool nimg = (unsigned)f0n < (unsigned)F && r0n < kImageRows;
+            const uint32_t last31 = nimg ? ring + ((t + 2) & (kRing - 1)) * R::kSegPitch : zeros;
+            const uint32_t last = lane == 31 ? last31 : off + 16 * (R::kChunks - 1);
 #pragma unroll
             for (int q = 0; q < R::kChunks - 1; ++q) {
                 const uint4 v = lds128(off + 16 * q);

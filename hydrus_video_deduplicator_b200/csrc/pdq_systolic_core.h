@@ -32,16 +32,18 @@
 //     The row prologue (pixels 0, 1 fed without output) is computed by lane 31 one step ahead in the two slots
 //     where its own row has only zeros left, and rides the rotate-shuffle into lane 0.
 //   * column chains: feeding row r yields output row r - 2; history slot = step & 3 (static after unrolling
-//     the step loop by 4).  P2 outputs rows 0 and 510 (divisor 3) are fixed up at r = 2 and r = 512; P4 is fed
-//     P3 rows r - 2 for 2 <= r <= 512 (zeros otherwise) and emits decimated row i at r = 8 i + 8.
+//     the step loop by 4).  P2 outputs rows 0 and 510 (divisor 3) are fixed up at r = 2 and r = 512.  P3 and P4
+//     run ONE STEP BEHIND P2 (so that the two serial row chains of a step, P1 of row r and P3 of P2-row r - 3,
+//     are independent and interleave in one basic block): P4 is fed P3 rows r - 3 for 3 <= r <= 513 (zeros
+//     otherwise) and emits decimated row i at r = 8 i + 9.
 //   * deferred power-of-two scaling as in pdq_fused2_core.h: planes stay unscaled (x4 per pass), divisor-3
 //     outputs become 4 * div3(s), the single multiply by 2^-8 happens on the 4096 emitted values.
 //
 // Raw staging.  Stream row s of lane group G' = l >> 2 (4 lanes, 192 + 16 bytes of the row) lives in slot s & 15
 // of that group's ring; TMA boxes of 4 stream rows x kSegPitch bytes, one per group per EVENT E covering the
 // group's stream rows 4 E - 4 G' .. + 3 (time-shifted per group: a group only ever holds the rows its own lanes
-// still need, which is what lets a 16-row ring absorb the 32-row skew).  ISSUE(E) at step 4 E - 9, WAIT(E) at step
-// 4 E - 1: eight steps of lead, two events in flight.
+// still need, which is what lets a 16-row ring absorb the 32-row skew).  ISSUE(E) at step 4 E - 10, WAIT(E) at step
+// 4 E - 2: eight steps of lead, two events in flight.  (A step reads the windows of the NEXT step's rows.)
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -79,6 +81,31 @@ VPDQS_HD float bits_to_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f;
 VPDQS_HD uint32_t byte_splice(uint32_t word, int k) { return 0x4B000000u | ((word >> (8 * k)) & 0xFFu); }
 #endif
 
+// packed fp32 pairs (sm_100a FADD2 / FFMA2: one instruction, two independent IEEE-RN results -- bit-identical to two
+// scalar operations)
+struct alignas(8) F2 {
+    float x, y;
+};
+#if defined(__CUDA_ARCH__)
+VPDQS_HD F2 f2_add(F2 a, F2 b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return F2{r.x, r.y};
+}
+VPDQS_HD F2 f2_sub(F2 a, F2 b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+    return F2{r.x, r.y};
+}
+VPDQS_HD F2 f2_fma(F2 a, F2 b, F2 c) {
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    return F2{r.x, r.y};
+}
+#else
+VPDQS_HD F2 f2_add(F2 a, F2 b) { return F2{fadd(a.x, b.x), fadd(a.y, b.y)}; }
+VPDQS_HD F2 f2_sub(F2 a, F2 b) { return F2{fsub(a.x, b.x), fsub(a.y, b.y)}; }
+VPDQS_HD F2 f2_fma(F2 a, F2 b, F2 c) { return F2{ffma(a.x, b.x, c.x), ffma(a.y, b.y, c.y)}; }
+#endif
+VPDQS_HD F2 f2_splat(float v) { return F2{v, v}; }
+
 // v / 3.0f, correctly rounded, branch free (Markstein; equal to IEEE division for every finite positive float,
 // tests/emu/div3_check.c), and invariant under power-of-two scaling of v
 VPDQS_HD float div3(float v) {
@@ -97,9 +124,11 @@ constexpr int kRing = 16;            // stream rows per group ring
 constexpr int kBoxRows = 4;          // stream rows per TMA box
 constexpr int kGroupLanes = 4;
 constexpr int kGroups = 32 / kGroupLanes;  // 8
-constexpr int kFirstStep = -4;       // the step loop starts here (a multiple of 4; steps < 0 only run lane 31's prologue)
-constexpr int kIssueLead = 9;        // ISSUE(E) at step 4 E - 9
-constexpr int kWaitLead = 1;         // WAIT(E)  at step 4 E - 1
+constexpr int kFirstStep = -4;       // the step loop starts here (a multiple of 4; steps < 0 only prepare lane 0's first row)
+constexpr int kIssueLead = 10;       // ISSUE(E) at step 4 E - 10
+constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
+                                     // computed one step ahead, as filler work for the serial chains)
+constexpr int kEventPhase = 2;       // both happen in the steps with (step & 3) == 2
 
 template <int CH>  // 3: RGB24, 1: 8-bit gray (== R = G = B)
 struct Raw {
@@ -129,11 +158,11 @@ template <int CH>
 VPDQS_HD int box_ring_offset(int g, int s0) { return g * Raw<CH>::kGroupRingBytes + (s0 & (kRing - 1)) * Raw<CH>::kSegPitch; }
 template <int CH>
 VPDQS_HD int box_x(int g) { return g * Raw<CH>::kSegBytes; }
-// last step of a warp that owns F frames: lane 31 feeds stream row 516 (F - 1) + 512 (the one drain row the last
-// frame needs)
-VPDQS_HD int last_step(int F) { return kStepsPerFrame * (F - 1) + kImageRows + 31; }
+// last step of a warp that owns F frames: lane 31 at stream row 516 (F - 1) + 513 (P3 / P4 run one step behind P2,
+// whose last output row 510 appears at row 512)
+VPDQS_HD int last_step(int F) { return kStepsPerFrame * (F - 1) + kImageRows + 1 + 31; }
 // events issued before the step loop starts
-VPDQS_HD int first_loop_event() { return (kFirstStep + kIssueLead + 3) / 4; }  // ISSUE(E) step 4E-9 >= kFirstStep  ->  E >= 2
+VPDQS_HD int first_loop_event() { return (kFirstStep + kEventPhase + kIssueLead) / 4; }  // = 2
 
 struct RowChain {  // running sum over a row, window 4: s + the last four inputs (h0 oldest)
     float s, h0, h1, h2, h3;
@@ -147,125 +176,150 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
 }
 
 struct LaneState {
-    float s2[kCols];      // P2 running sums, one per owned column
-    float h2[4][kCols];   // P2 histories, slot = step & 3
-    float s4[2];          // P4 running sums of the two decimated columns 2l, 2l+1
-    float h4[4][2];
-    RowChain in1, in3;    // chain states handed over by lane l - 1 for THIS step's row (P1; P3)
-    int r, f;             // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
+    F2 s2[kCols / 2];      // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start of
+                           // a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
+                           // (one set of registers for both: see the tail of lane_step for the divisor-3 rows)
+    F2 h2[4][kCols / 2];   // P2 histories (the last four inputs), slot = step & 3
+    F2 x[kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous step
+    F2 s4;                 // P4 running sums of the two decimated columns 2l, 2l+1
+    F2 h4[4];
+    RowChain in1, in3;     // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
+    int r, f;              // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
     VPDQS_HD void init(int lane) {
         VPDQS_UNROLL
-        for (int k = 0; k < kCols; ++k) {
-            s2[k] = 0.0f;
-            h2[0][k] = h2[1][k] = h2[2][k] = h2[3][k] = 0.0f;
+        for (int p = 0; p < kCols / 2; ++p) {
+            s2[p] = f2_splat(0.0f);
+            h2[0][p] = h2[1][p] = h2[2][p] = h2[3][p] = f2_splat(0.0f);
+            x[p] = f2_splat(0.0f);
         }
-        s4[0] = s4[1] = 0.0f;
+        s4 = f2_splat(0.0f);
         VPDQS_UNROLL
-        for (int j = 0; j < 4; ++j) h4[j][0] = h4[j][1] = 0.0f;
+        for (int j = 0; j < 4; ++j) h4[j] = f2_splat(0.0f);
         in1 = row_zero();
         in3 = row_zero();
         // stream row of lane l at the first step = kFirstStep - l < 0: rows of the virtual frame -1 (never live)
         f = -1;
         r = kStepsPerFrame + kFirstStep - lane;
     }
-    VPDQS_HD bool reads_image(int n_frames) const { return (unsigned)f < (unsigned)n_frames && r < kImageRows; }
-    VPDQS_HD void advance() {
-        if (++r == kStepsPerFrame) {
-            r = 0;
-            ++f;
-        }
+    // does the NEXT step of this lane read an image row?
+    VPDQS_HD bool next_reads_image(int n_frames) const {
+        const bool wrap = r + 1 == kStepsPerFrame;
+        const int rn = wrap ? 0 : r + 1, fn = wrap ? f + 1 : f;
+        return (unsigned)fn < (unsigned)n_frames && rn < kImageRows;
     }
 };
 
-// luma of the pixel whose first byte sits at byte offset b0 of the little-endian word array w.  u8 -> fp32 product
-// without an I2F: the byte is spliced into the mantissa of 2^23 (PRMT): M = 2^23 + b exactly;
-// fma(c, M, -c * 2^23) = RN(c * b), bit-identical to __fmul_rn(c, (float)b) (c * 2^23 is exact).  CH == 1: the
-// same three-term expression on one byte (SURVEY.md 8 note a-1).
-template <int CH, int N>
-VPDQS_HD float luma_at(const uint32_t (&w)[N], int b0) {
-    const float cr = 0.299f, cg = 0.587f, cb = 0.114f, two23 = 8388608.0f;
-    const int b1 = CH == 3 ? b0 + 1 : b0, b2 = CH == 3 ? b0 + 2 : b0;
-    const float mr = bits_to_float(byte_splice(w[b0 >> 2], b0 & 3));
-    const float mg = CH == 3 ? bits_to_float(byte_splice(w[b1 >> 2], b1 & 3)) : mr;
-    const float mb = CH == 3 ? bits_to_float(byte_splice(w[b2 >> 2], b2 & 3)) : mr;
-    const float r = ffma(cr, mr, -(cr * two23));
-    const float g = ffma(cg, mg, -(cg * two23));
-    const float b = ffma(cb, mb, -(cb * two23));
-    return fadd(fadd(r, g), b);  // (0.299 R + 0.587 G) + 0.114 B
+// M = 2^23 + byte: the byte at offset b of the little-endian word array spliced into the mantissa of 2^23 (PRMT)
+template <int N>
+VPDQS_HD float magic_at(const uint32_t (&w)[N], int b) {
+    return bits_to_float(byte_splice(w[b >> 2], b & 3));
 }
 
-// One lane, one step.  J = step & 3 (history slot).  w = the lane's raw window of its stream row (zeros when the
-// row is not an image row); for lane 31 the LAST chunk is instead the first 16 bytes of the row lane 0 works on in
-// the NEXT step (zeros if that is not an image row).
+// luma of the two pixels whose first bytes sit at byte offsets b0 and b0 + CH of w, as one packed pair.
+// u8 -> fp32 product without an I2F: fma(c, M, -c * 2^23) = RN(c * b), bit-identical to __fmul_rn(c, (float)b)
+// (c * 2^23 is exact).  CH == 1: the same three-term expression on one byte (SURVEY.md 8 note a-1).
+template <int CH, int N>
+VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
+    const float cr = 0.299f, cg = 0.587f, cb = 0.114f, two23 = 8388608.0f;
+    const int p0 = b0, p1 = b0 + CH;
+    const F2 mr{magic_at(w, p0), magic_at(w, p1)};
+    const F2 mg = CH == 3 ? F2{magic_at(w, p0 + 1), magic_at(w, p1 + 1)} : mr;
+    const F2 mb = CH == 3 ? F2{magic_at(w, p0 + 2), magic_at(w, p1 + 2)} : mr;
+    const F2 r = f2_fma(f2_splat(cr), mr, f2_splat(-(cr * two23)));
+    const F2 g = f2_fma(f2_splat(cg), mg, f2_splat(-(cg * two23)));
+    const F2 b = f2_fma(f2_splat(cb), mb, f2_splat(-(cb * two23)));
+    return f2_add(f2_add(r, g), b);  // (0.299 R + 0.587 G) + 0.114 B
+}
+
+// One lane, one step.  J = step & 3 (history slot).  w = the raw window of the lane's NEXT stream row (zeros when
+// that row is not an image row); for lane 31 the LAST chunk is instead the first 16 bytes of the row lane 0 works
+// on TWO steps ahead (zeros if that is not an image row).
+//
+// The step has one branch-free main block in which the two serial chains -- P1 over this step's row r and P3 over
+// the P2 outputs of the PREVIOUS step (output row r - 3) -- start with every input ready and run side by side with
+// the independent work (P2, and the lumas of the NEXT step's row) that fills their latency, and a tail with the
+// rare per-lane cases (divisor-3 rows, frame start).
 // out1 / out3: the chain states to hand to lane l + 1 (lane 31 -> lane 0: the next row's initial states).
 // emit(frame, i, v0, v1): decimated row i of columns 2l, 2l+1 is final.
 template <int CH, int J, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
     const int r = L.r;
-    if (r == 0) {  // new frame: the histories were flushed by the four zero rows, the sums hold rounding residue
-        VPDQS_UNROLL
-        for (int k = 0; k < kCols; ++k) L.s2[k] = 0.0f;
-    }
-    // ---- P1 (row pass 1, along the lanes) + P2 (column pass 1, private) ----
-    RowChain c1 = L.in1;
-    float y2[kCols];
-    float xa = 0.0f, xb = 0.0f;
-    VPDQS_UNROLL
-    for (int k = 0; k < kCols; ++k) {
-        float x = luma_at<CH>(w, Raw<CH>::kSkip + CH * k);  // pixel 16 l + 2 + k
-        if (k == 14) xa = x;
-        if (k == 15) xb = x;
-        if (k >= 14 && lane == 31) x = 0.0f;  // pixels 512, 513: the drain of the row
-        float v = row_feed(c1, x);            // output column 16 l + k, unscaled (x4)
-        if (k == 0 && lane == 0) v = edge3(v);    // column 0: divisor 3
-        if (k == 14 && lane == 31) v = edge3(v);  // column 510: divisor 3 (column 511 feeds no decimated output)
-        const float old = L.h2[J][k];
-        float s = fadd(L.s2[k], v);
-        s = fsub(s, old);
-        L.h2[J][k] = v;
-        L.s2[k] = s;
-        y2[k] = s;  // output row r - 2 of column 16 l + k, unscaled (x16)
-    }
-    if (r == 2 || r == kImageRows) {  // output rows 0 and 510: divisor 3
-        VPDQS_UNROLL
-        for (int k = 0; k < kCols; ++k) y2[k] = edge3(y2[k]);
-        if (r == 2) L.s4[0] = L.s4[1] = 0.0f;  // P4 starts here; its histories were flushed by 5 zero feeds
-    }
-    // ---- P3 (row pass 2, along the lanes): only the decimated columns 8 j + 4 are kept ----
-    RowChain c3 = L.in3;
+    RowChain c1 = L.in1, c3 = L.in3;
+    F2 xn[kCols / 2];
     float z0 = 0.0f, z1 = 0.0f;
+    // lane 31: its last two lumas are the NEXT row's pixels 0, 1 (its own row has only the drain zeros left there)
+    const float xa = L.x[7].x, xb = L.x[7].y;
     VPDQS_UNROLL
-    for (int k = 0; k < kCols; ++k) {
-        const float v = row_feed(c3, y2[k]);  // output column 16 l + k - 2
-        if (k == 6) z0 = v;
-        if (k == 14) z1 = v;
+    for (int p = 0; p < kCols / 2; ++p) {
+        const int k = 2 * p;
+        xn[p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
+        F2 x = L.x[p];
+        if (p == 7 && lane == 31) x = f2_splat(0.0f);
+        // P1: row pass 1 along the lanes -> output columns 16 l + k, + 1 (unscaled, x4)
+        float v0 = row_feed(c1, x.x);
+        if (p == 0 && lane == 0) v0 = edge3(v0);   // column 0: divisor 3
+        if (p == 7 && lane == 31) v0 = edge3(v0);  // column 510: divisor 3 (column 511 feeds no decimated output)
+        const float v1 = row_feed(c1, x.y);
+        // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
+        const F2 v{v0, v1};
+        const F2 old = L.h2[J][p], prev = L.s2[p];
+        F2 s = f2_add(prev, v);
+        s = f2_sub(s, old);
+        L.h2[J][p] = v;
+        L.s2[p] = s;
+        // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
+        // decimated columns 8 j + 4 are kept
+        const float u0 = row_feed(c3, prev.x);
+        if (k == 6) z0 = u0;
+        if (k == 14) z1 = u0;
+        row_feed(c3, prev.y);
     }
-    // ---- P4 (column pass 2, private), fed P3 row r - 2 ----
-    const bool zvalid = r >= 2 && r <= kImageRows;
-    if (!zvalid) z0 = z1 = 0.0f;
-    float o0, o1;
+    // P4: column pass 2, private, fed P3 row r - 3 (real for 3 <= r <= 513, zeros otherwise) -> output row r - 5
     {
-        const float old0 = L.h4[J][0], old1 = L.h4[J][1];
-        float s0 = fadd(L.s4[0], z0), s1 = fadd(L.s4[1], z1);
-        s0 = fsub(s0, old0);
-        s1 = fsub(s1, old1);
-        L.h4[J][0] = z0;
-        L.h4[J][1] = z1;
-        L.s4[0] = o0 = s0;
-        L.s4[1] = o1 = s1;
+        const bool zvalid = r >= 3 && r <= kImageRows + 1;
+        const F2 z = zvalid ? F2{z0, z1} : f2_splat(0.0f);
+        const F2 old = L.h4[J];
+        F2 s = f2_add(L.s4, z);
+        s = f2_sub(s, old);
+        L.h4[J] = z;
+        L.s4 = s;
+        if ((unsigned)L.f < (unsigned)n_frames && r >= 9 && (r & 7) == 1)  // output row r - 5 = 8 i + 4
+            emit(L.f, ((r - 1) >> 3) - 1, fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
     }
-    if ((unsigned)L.f < (unsigned)n_frames && r >= 8 && (r & 7) == 0)  // output row r - 4 = 8 i + 4
-        emit(L.f, (r >> 3) - 1, fmul(o0, 0.00390625f), fmul(o1, 0.00390625f));  // the deferred 4^-4
-
-    // ---- hand-over ----
+    // hand-over
     out1 = c1;
     out3 = c3;
     if (lane == 31) {  // -> lane 0, next row: the chain after the prologue pixels 0, 1 (fed without output) / a fresh chain
         out1 = RowChain{fadd(xa, xb), 0.0f, 0.0f, xa, xb};
         out3 = row_zero();
     }
-    L.advance();
+    // ---- tail: the rare per-lane cases ----
+    // P2 output rows 0 (r = 2) and 510 (r = 512) have divisor 3.  The sums double as P3's input of the next step, so
+    // the fix-up is done IN PLACE (no second set of registers, no copies in the common path): after row 510 the sums
+    // are dead anyway (zero rows follow, reset at the frame start); after row 0 the next step's P2 update runs on the
+    // fixed-up value and is wrong for this lane -- its tail (r = 3) rebuilds the sums from the history, which at that
+    // point holds exactly rows 0..3: ((v0 + v1) + v2) + v3, the very operations of the running sum (its
+    // subtractions are all of zeros there).
+    if (r == 2 || r == kImageRows) {
+        VPDQS_UNROLL
+        for (int p = 0; p < kCols / 2; ++p) L.s2[p] = F2{edge3(L.s2[p].x), edge3(L.s2[p].y)};
+        // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
+        if (r == 2) L.s4 = f2_splat(0.0f);
+    }
+    if (r == 3) {
+        VPDQS_UNROLL
+        for (int p = 0; p < kCols / 2; ++p)
+            L.s2[p] = f2_add(f2_add(f2_add(L.h2[(J + 1) & 3][p], L.h2[(J + 2) & 3][p]), L.h2[(J + 3) & 3][p]), L.h2[J][p]);
+    }
+    VPDQS_UNROLL
+    for (int p = 0; p < kCols / 2; ++p) L.x[p] = xn[p];
+    if (++L.r == kStepsPerFrame) {  // next step starts a new frame: the P2 histories were flushed by the four zero
+        L.r = 0;                    // rows, the sums hold rounding residue
+        ++L.f;
+        VPDQS_UNROLL
+        for (int p = 0; p < kCols / 2; ++p) L.s2[p] = f2_splat(0.0f);
+    }
 }
 
 }  // namespace vpdq_sys

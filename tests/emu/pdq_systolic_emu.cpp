@@ -77,14 +77,14 @@ template <int CH, int J>
 void step_all(WarpSim<CH>& W, LaneState* st, int t, float* a64, long long f_first) {
     using R = Raw<CH>;
     RowChain out1[32], out3[32];
-    const int next0 = t + 1;  // stream row of lane 0 in the next step
+    const int next0 = t + 2;  // stream row of lane 0 two steps ahead (lane 31 prepares its prologue pixels)
     const bool next0_image = next0 >= 0 && next0 / kStepsPerFrame < W.F && next0 % kStepsPerFrame < kImageRows;
     for (int lane = 0; lane < 32; ++lane) {
         uint32_t w[R::kWords];
         memset(w, 0, sizeof w);
-        if (st[lane].reads_image(W.F)) {
-            const int s = t - lane;
-            if (s != st[lane].f * kStepsPerFrame + st[lane].r) ++W.errors;
+        if (st[lane].next_reads_image(W.F)) {  // the window of the NEXT step's row
+            const int s = t + 1 - lane;
+            if (s != st[lane].f * kStepsPerFrame + st[lane].r + 1) ++W.errors;
             for (int q = 0; q < R::kChunks - (lane == 31 ? 1 : 0); ++q) W.read_chunk(lane, s, q, w + 4 * q);
         }
         if (lane == 31 && next0_image) W.read_chunk(0, next0, 0, w + 4 * (R::kChunks - 1));
@@ -121,7 +121,7 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
         int issued = first_loop_event() - 1, waited = -1;
         const int t_last = last_step(F);
         for (int t = kFirstStep; t <= t_last; ++t) {
-            if ((t & 3) == 3) {
+            if ((t & 3) == kEventPhase) {
                 const int Ew = (t + kWaitLead) / 4, Ei = (t + kIssueLead) / 4;
                 if (Ew >= 0) { W->wait(Ew); waited = Ew; }
                 W->issue(Ei);
