@@ -4,14 +4,17 @@
 // no CPU implementation of anything here.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
+#include "hash_service.h"
 
 namespace vpdq {
 
@@ -66,78 +69,159 @@ struct DeviceGuard {
 using namespace vpdq;
 
 // ====================================================================================================
-// streaming hasher
+// streaming hasher: every handle is bookkeeping on top of the per-device submission service (hash_service.h)
 // ====================================================================================================
 namespace {
-constexpr int kSlots = 3;         // pinned staging ring depth
-constexpr int kSlotFrames = 32;   // frames per staged batch (25 MB RGB)
 
-struct Slot {
-    uint8_t* h_frames = nullptr;  // pinned
-    uint8_t* d_frames = nullptr;
-    uint8_t* h_hash = nullptr;    // pinned results
-    int32_t* h_quality = nullptr;
-    uint8_t* d_hash = nullptr;
-    int32_t* d_quality = nullptr;
-    cudaEvent_t done = nullptr;
-    int filled = 0;     // frames memcpy'd into h_frames, not yet submitted
-    int in_flight = 0;  // frames submitted, results not yet collected
+// The CUDA side of the service: pinned + device arenas, a copy stream and a compute stream.
+struct CudaDev {
+    struct Event {
+        cudaEvent_t ev = nullptr;
+    };
+    int device = 0, channels = 3;
+    size_t frame_bytes = 0, n_slots = 0;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t uploaded = nullptr;
+    uint8_t *h_frames = nullptr, *d_frames = nullptr, *h_hash = nullptr, *d_hash = nullptr;
+    int32_t *h_quality = nullptr, *d_quality = nullptr;
+    int* h_flags = nullptr;  // pinned: the kernels' "a TMA wait gave up" flags of the last retired launch
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::vector<cudaEvent_t> pool;
+    std::mutex pool_mu;
+
+    int alloc(size_t n, size_t fb, uint8_t** hf, uint8_t** df, uint8_t** hh, int32_t** hq) {
+        n_slots = n;
+        frame_bytes = fb;
+        VPDQ_CUDA(cudaSetDevice(device));
+        VPDQ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        VPDQ_CUDA(cudaStreamCreateWithFlags(&compute_stream, cudaStreamNonBlocking));
+        VPDQ_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+        VPDQ_CUDA(cudaHostAlloc(&h_frames, n * fb, cudaHostAllocDefault));
+        VPDQ_CUDA(cudaMalloc(&d_frames, n * fb));
+        VPDQ_CUDA(cudaHostAlloc(&h_hash, n * 32, cudaHostAllocDefault));
+        VPDQ_CUDA(cudaHostAlloc(&h_quality, n * sizeof(int32_t), cudaHostAllocDefault));
+        VPDQ_CUDA(cudaHostAlloc(&h_flags, 4 * sizeof(int), cudaHostAllocDefault));
+        memset(h_flags, 0, 4 * sizeof(int));
+        VPDQ_CUDA(cudaMalloc(&d_hash, n * 32));
+        VPDQ_CUDA(cudaMalloc(&d_quality, n * sizeof(int32_t)));
+        scratch_bytes = n * fused_scratch_per_frame();
+        VPDQ_CUDA(cudaMalloc(&d_scratch, scratch_bytes));
+        *hf = h_frames;
+        *df = d_frames;
+        *hh = h_hash;
+        *hq = h_quality;
+        return VPDQ_B200_OK;
+    }
+    void thread_init() { cudaSetDevice(device); }
+    int upload(uint8_t* d_dst, const uint8_t* h_src, size_t bytes) {
+        VPDQ_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, copy_stream));
+        return VPDQ_B200_OK;
+    }
+    int launch(size_t first_slot, size_t n, Event* out) {
+        VPDQ_CUDA(cudaEventRecord(uploaded, copy_stream));
+        VPDQ_CUDA(cudaStreamWaitEvent(compute_stream, uploaded, 0));
+        int rc = pdq_launch(d_frames + first_slot * frame_bytes, channels, (int64_t)n, d_hash + first_slot * 32,
+                            d_quality + first_slot, nullptr, nullptr, d_scratch, scratch_bytes, compute_stream);
+        if (rc) return rc;
+        VPDQ_CUDA(cudaMemcpyAsync(h_hash + first_slot * 32, d_hash + first_slot * 32, n * 32, cudaMemcpyDeviceToHost,
+                                  compute_stream));
+        VPDQ_CUDA(cudaMemcpyAsync(h_quality + first_slot, d_quality + first_slot, n * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, compute_stream));
+        rc = pdq_timeout_flags_async(h_flags, compute_stream);
+        if (rc) return rc;
+        cudaEvent_t ev = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(pool_mu);
+            if (!pool.empty()) {
+                ev = pool.back();
+                pool.pop_back();
+            }
+        }
+        if (!ev) VPDQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        VPDQ_CUDA(cudaEventRecord(ev, compute_stream));
+        out->ev = ev;
+        return VPDQ_B200_OK;
+    }
+    bool is_done(Event& e, int* rc) {
+        const cudaError_t q = cudaEventQuery(e.ev);
+        if (q == cudaErrorNotReady) return false;
+        if (q != cudaSuccess) *rc = cuda_fail(q, "cudaEventQuery (hash service)");
+        return true;
+    }
+    int launch_status() {
+        if (h_flags[0] | h_flags[1] | h_flags[2]) {
+            set_error("a TMA copy inside the PDQ kernel never completed (flags %d %d %d): results invalid", h_flags[0],
+                      h_flags[1], h_flags[2]);
+            return VPDQ_B200_ERR_CUDA;
+        }
+        return VPDQ_B200_OK;
+    }
+    void release(Event& e) {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        pool.push_back(e.ev);
+        e.ev = nullptr;
+    }
+    void idle_pause(bool gpu_busy) {
+        (void)gpu_busy;
+        std::this_thread::yield();
+    }
 };
+
+using Service = vpdq_service::HashService<CudaDev>;
+struct ServiceSlot {
+    std::mutex mu;
+    CudaDev* dev = nullptr;
+    Service* svc = nullptr;
+    int rc = 0;
+};
+ServiceSlot g_services[64][2];  // [device][channels == 1]
+
+int env_int(const char* name, int fallback, int lo, int hi) {
+    const char* e = getenv(name);
+    if (!e || !*e) return fallback;
+    const long v = strtol(e, nullptr, 10);
+    return v < lo ? lo : (v > hi ? hi : (int)v);
+}
+
+// the service of (device, channels); created on first use and kept for the life of the process
+int get_service(int device, int channels, Service** out) {
+    if (device < 0 || device >= 64) {
+        set_error("device index %d out of range", device);
+        return VPDQ_B200_ERR_INVALID;
+    }
+    ServiceSlot& slot = g_services[device][channels == 1];
+    std::lock_guard<std::mutex> lk(slot.mu);
+    if (!slot.svc && slot.rc == 0) {
+        const unsigned cores = std::thread::hardware_concurrency();
+        vpdq_service::Config cfg;
+        cfg.frame_bytes = (size_t)kPlane * channels;
+        cfg.arena_frames = env_int("VPDQ_B200_ARENA_FRAMES", 256, 8, 4096);
+        cfg.copy_workers = env_int("VPDQ_B200_COPY_THREADS", (int)(cores >= 16 ? 8 : cores >= 4 ? cores / 2 : 2), 1, 64);
+        cfg.copy_parts = 4;
+        cfg.max_launch = cfg.arena_frames;
+        cfg.max_inflight = 2;
+        slot.dev = new CudaDev;
+        slot.dev->device = device;
+        slot.dev->channels = channels;
+        slot.svc = new Service(slot.dev, cfg);
+        slot.rc = slot.svc->start();
+        if (slot.rc) {  // (arenas stay allocated as far as they got; the error is sticky for this process)
+            slot.svc = nullptr;
+        }
+    }
+    if (slot.rc) return slot.rc;
+    *out = slot.svc;
+    return VPDQ_B200_OK;
+}
 }  // namespace
 
 struct vpdq_b200_hasher {
     int device = 0, channels = 3;
     size_t frame_bytes = 0;
-    cudaStream_t stream = nullptr;
-    void* d_scratch = nullptr;
-    size_t scratch_bytes = 0;
-    Slot slots[kSlots];
-    int cur = 0;
-    int64_t pushed = 0;
-    std::vector<uint8_t> hashes;    // collected, in push order
-    std::vector<int32_t> quality;
-    std::mutex mu;
+    Service* svc = nullptr;
+    vpdq_service::HasherState st;
 };
-
-static void hasher_free(vpdq_b200_hasher* h) {
-    for (Slot& s : h->slots) {
-        if (s.h_frames) cudaFreeHost(s.h_frames);
-        if (s.d_frames) cudaFree(s.d_frames);
-        if (s.h_hash) cudaFreeHost(s.h_hash);
-        if (s.h_quality) cudaFreeHost(s.h_quality);
-        if (s.d_hash) cudaFree(s.d_hash);
-        if (s.d_quality) cudaFree(s.d_quality);
-        if (s.done) cudaEventDestroy(s.done);
-    }
-    if (h->d_scratch) cudaFree(h->d_scratch);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    delete h;
-}
-
-// wait for a slot's batch and move its results to the host vectors
-static int slot_collect(vpdq_b200_hasher* h, Slot& s) {
-    if (s.in_flight == 0) return VPDQ_B200_OK;
-    VPDQ_CUDA(cudaEventSynchronize(s.done));
-    h->hashes.insert(h->hashes.end(), s.h_hash, s.h_hash + (size_t)s.in_flight * 32);
-    h->quality.insert(h->quality.end(), s.h_quality, s.h_quality + s.in_flight);
-    s.in_flight = 0;
-    return VPDQ_B200_OK;
-}
-
-static int slot_submit(vpdq_b200_hasher* h, Slot& s) {
-    if (s.filled == 0) return VPDQ_B200_OK;
-    const int n = s.filled;
-    VPDQ_CUDA(cudaMemcpyAsync(s.d_frames, s.h_frames, (size_t)n * h->frame_bytes, cudaMemcpyHostToDevice, h->stream));
-    int rc = pdq_launch(s.d_frames, h->channels, n, s.d_hash, s.d_quality, nullptr, nullptr, h->d_scratch,
-                        h->scratch_bytes, h->stream);
-    if (rc) return rc;
-    VPDQ_CUDA(cudaMemcpyAsync(s.h_hash, s.d_hash, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
-    VPDQ_CUDA(cudaMemcpyAsync(s.h_quality, s.d_quality, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    VPDQ_CUDA(cudaEventRecord(s.done, h->stream));
-    s.in_flight = n;
-    s.filled = 0;
-    return VPDQ_B200_OK;
-}
 
 extern "C" {
 
@@ -165,6 +249,13 @@ int vpdq_b200_debug_flags(int device, int* flags) {
     if (rc) return rc;
     *flags = f1 | f2 | f3;
     return VPDQ_B200_OK;
+}
+
+int vpdq_b200_debug_force_timeout(int device, int value) {
+    DeviceGuard g(device);
+    if (g.rc) return g.rc;
+    VPDQ_CUDA(cudaDeviceSynchronize());
+    return pdq_force_timeout_flags(value);
 }
 
 int vpdq_b200_set_pdq_impl(int impl) { return pdq_set_impl(impl); }
@@ -345,67 +436,53 @@ int vpdq_b200_hasher_create(int device, int width, int height, int channels, int
     if (rc) return rc;
     DeviceGuard g(device);
     if (g.rc) return g.rc;
+    int dev = 0;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    Service* svc = nullptr;
+    rc = get_service(dev, channels, &svc);  // allocates the shared arenas on first use; a hasher itself owns nothing
+    if (rc) return rc;
     vpdq_b200_hasher* h = new (std::nothrow) vpdq_b200_hasher;
     if (!h) return VPDQ_B200_ERR_NOMEM;
-    cudaError_t e = cudaGetDevice(&h->device);
+    h->device = dev;
     h->channels = channels;
     h->frame_bytes = (size_t)kPlane * channels;
-    h->scratch_bytes = pdq_scratch_bytes(kSlotFrames);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_scratch, h->scratch_bytes);
-    for (int i = 0; i < kSlots && e == cudaSuccess; ++i) {
-        Slot& s = h->slots[i];
-        e = cudaMalloc(&s.d_frames, kSlotFrames * h->frame_bytes);
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_hash, kSlotFrames * 32);
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_quality, kSlotFrames * sizeof(int32_t));
-        if (e == cudaSuccess) e = cudaHostAlloc(&s.h_hash, kSlotFrames * 32, cudaHostAllocDefault);
-        if (e == cudaSuccess) e = cudaHostAlloc(&s.h_quality, kSlotFrames * sizeof(int32_t), cudaHostAllocDefault);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
-        // the big pinned frame buffer is allocated on first use (most videos never need slots 1, 2)
-    }
-    if (e != cudaSuccess) {
-        hasher_free(h);
-        return cuda_fail(e, "vpdq_b200_hasher_create");
-    }
+    h->svc = svc;
     *out = h;
     return VPDQ_B200_OK;
 }
 
-int vpdq_b200_hasher_push(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames) {
+static int hasher_push(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames, bool wait_copied) {
     if (!h || n_frames < 0 || (n_frames > 0 && !h_frames)) {
         set_error("hasher_push: invalid argument");
         return VPDQ_B200_ERR_INVALID;
     }
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard g(h->device);
-    if (g.rc) return g.rc;
-    for (int64_t f = 0; f < n_frames;) {
-        Slot& s = h->slots[h->cur];
-        if (s.filled == 0 && s.in_flight) {  // back-pressure: block until this slot's batch is done
-            int rc = slot_collect(h, s);
-            if (rc) return rc;
-        }
-        if (!s.h_frames) VPDQ_CUDA(cudaHostAlloc(&s.h_frames, kSlotFrames * h->frame_bytes, cudaHostAllocDefault));
-        int64_t take = kSlotFrames - s.filled;
-        if (take > n_frames - f) take = n_frames - f;
-        memcpy(s.h_frames + (size_t)s.filled * h->frame_bytes, h_frames + (size_t)f * h->frame_bytes,
-               (size_t)take * h->frame_bytes);
-        s.filled += (int)take;
-        f += take;
-        h->pushed += take;
-        if (s.filled == kSlotFrames) {
-            int rc = slot_submit(h, s);
-            if (rc) return rc;
-            h->cur = (h->cur + 1) % kSlots;
-        }
+    if (n_frames == 0) return VPDQ_B200_OK;
+    const int rc = h->svc->push(&h->st, h_frames, n_frames, wait_copied);
+    if (rc) {
+        set_error("hasher_push: the hashing service of device %d failed (%d)", h->device, rc);
+        return rc < 0 ? rc : VPDQ_B200_ERR_CUDA;
     }
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_hasher_push(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames) {
+    return hasher_push(h, h_frames, n_frames, true);
+}
+
+int vpdq_b200_hasher_push_nocopy(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames) {
+    return hasher_push(h, h_frames, n_frames, false);
+}
+
+int vpdq_b200_hasher_consumed(vpdq_b200_hasher* h, int64_t* n) {
+    if (!h || !n) return VPDQ_B200_ERR_INVALID;
+    *n = h->st.consumed.load(std::memory_order_acquire);
     return VPDQ_B200_OK;
 }
 
 int vpdq_b200_hasher_pushed(vpdq_b200_hasher* h, int64_t* n) {
     if (!h || !n) return VPDQ_B200_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(h->mu);
-    *n = h->pushed;
+    std::lock_guard<std::mutex> lk(h->st.mu);
+    *n = h->st.pushed;
     return VPDQ_B200_OK;
 }
 
@@ -415,30 +492,34 @@ int vpdq_b200_hasher_finish(vpdq_b200_hasher* h, int quality_keep, uint8_t* h_ha
         set_error("hasher_finish: invalid argument");
         return VPDQ_B200_ERR_INVALID;
     }
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard g(h->device);
-    if (g.rc) return g.rc;
-    // submit the partial batch, then drain the ring in submission order (oldest = slot after cur)
-    int rc = slot_submit(h, h->slots[h->cur]);
-    if (rc) return rc;
-    for (int k = 1; k <= kSlots; ++k) {
-        rc = slot_collect(h, h->slots[(h->cur + k) % kSlots]);
-        if (rc) return rc;
-    }
-    const int64_t n = h->pushed;
+    const int err = h->svc->wait_all(&h->st);  // this hasher's frames only
+    std::lock_guard<std::mutex> lk(h->st.mu);
+    const int64_t n = h->st.pushed;
     int64_t kept = 0;
-    for (int64_t i = 0; i < n; ++i)
-        if (h->quality[i] >= quality_keep) {
-            if (kept < cap) memcpy(h_hashes + kept * 32, h->hashes.data() + i * 32, 32);
-            ++kept;
-        }
-    if (h_all_hashes && n) memcpy(h_all_hashes, h->hashes.data(), (size_t)n * 32);
-    if (h_all_quality && n) memcpy(h_all_quality, h->quality.data(), (size_t)n * sizeof(int32_t));
+    if (!err) {
+        for (int64_t i = 0; i < n; ++i)
+            if (h->st.quality[i] >= quality_keep) {
+                if (kept < cap) memcpy(h_hashes + kept * 32, h->st.hashes.data() + i * 32, 32);
+                ++kept;
+            }
+        if (h_all_hashes && n) memcpy(h_all_hashes, h->st.hashes.data(), (size_t)n * 32);
+        if (h_all_quality && n) memcpy(h_all_quality, h->st.quality.data(), (size_t)n * sizeof(int32_t));
+    }
     *n_kept = kept;
-    h->hashes.clear();
-    h->quality.clear();
-    h->pushed = 0;
-    h->cur = 0;
+    // reset: a healthy hasher is reusable (nothing of it is in flight any more); after an error the results are
+    // dropped and the error stays (the service of this device is broken for good: fail loudly, never guess)
+    h->st.hashes.clear();
+    h->st.quality.clear();
+    if (!err) {
+        h->st.pushed = 0;
+        h->st.done = 0;
+        h->st.consumed.store(0, std::memory_order_release);
+    }
+    if (err) {
+        set_error("hasher_finish: the hashing service of device %d failed (%d; a CUDA error or a TMA copy that never "
+                  "completed)", h->device, err);
+        return err < 0 ? err : VPDQ_B200_ERR_CUDA;
+    }
     if (kept > cap) {
         set_error("hasher_finish: %lld hashes kept but capacity is %lld", (long long)kept, (long long)cap);
         return VPDQ_B200_ERR_OVERFLOW;
@@ -448,11 +529,8 @@ int vpdq_b200_hasher_finish(vpdq_b200_hasher* h, int quality_keep, uint8_t* h_ha
 
 int vpdq_b200_hasher_destroy(vpdq_b200_hasher* h) {
     if (!h) return VPDQ_B200_OK;
-    {
-        DeviceGuard g(h->device);
-        if (h->stream) cudaStreamSynchronize(h->stream);
-        hasher_free(h);
-    }
+    h->svc->wait_all(&h->st);  // the service still refers to this hasher until its frames have retired
+    delete h;
     return VPDQ_B200_OK;
 }
 

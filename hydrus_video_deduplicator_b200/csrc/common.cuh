@@ -41,9 +41,13 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
 size_t fused_scratch_per_frame();
 int fused_jarosz_launch(const uint8_t* d_frames, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int fused_debug_flags(int* flags);
+int fused_timeout_flag_async(int* h_flag, cudaStream_t stream);
+int fused_force_timeout(int value);
 // the same, two frames per lane in packed fp32 pairs (pdq_fused2.cu) -- the default
 int fused2_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int fused2_debug_flags(int* flags);
+int fused2_timeout_flag_async(int* h_flag, cudaStream_t stream);
+int fused2_force_timeout(int value);
 // the warp-per-frame systolic kernel (pdq_systolic.cu): no shared-memory transposition between the passes
 int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream);
 int systolic_debug_flags(int* flags);
@@ -54,6 +58,10 @@ int systolic_timeout_flag_async(int* h_flag, cudaStream_t stream);
 int pdq_impl();
 int pdq_set_impl(int impl);
 int pdq_upload_tables();  // DCT matrix -> device (once per device)
+// the kernels' "a bounded TMA wait gave up" flags -> h_flags[0..2] (pinned), stream-ordered; nonzero = results of the
+// launches before it on this device are invalid.  Every host-pointer entry checks them at its synchronisation point.
+int pdq_timeout_flags_async(int* h_flags, cudaStream_t stream);
+int pdq_force_timeout_flags(int value);  // test hook
 const float* pdq_host_dct();
 
 // ---- POINT resize (resize_kernels.cu) ----------------------------------------------------------------

@@ -27,6 +27,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -68,6 +69,7 @@ class HashService {
         slots_.reset(new Slot[n]);
         for (size_t i = 0; i < n; ++i) slots_[i].parts_left.store(0);
         stop_ = false;
+        stop_atomic_.store(false, std::memory_order_release);
         pump_ = std::thread([this] { pump_main(); });
         for (int w = 0; w < cfg_.copy_workers; ++w) workers_.emplace_back([this] { worker_main(); });
         return 0;
@@ -78,6 +80,7 @@ class HashService {
             std::lock_guard<std::mutex> lk(mu_);
             if (stop_) return;
             stop_ = true;
+            stop_atomic_.store(true, std::memory_order_release);
         }
         cv_pump_.notify_all();
         cv_space_.notify_all();
@@ -247,6 +250,7 @@ class HashService {
                 std::lock_guard<std::mutex> hk(o->mu);
                 for (int64_t k = c; k < e; ++k) {
                     const Slot& s = slots_[k % A];
+                    if ((size_t)s.seq >= o->quality.size()) continue;  // the owner gave up on an errored run
                     memcpy(o->hashes.data() + (size_t)s.seq * 32, h_hash_ + (size_t)(k % A) * 32, 32);
                     o->quality[(size_t)s.seq] = h_quality_[k % A];
                 }

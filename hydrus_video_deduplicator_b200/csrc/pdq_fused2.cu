@@ -210,6 +210,15 @@ int fused2_debug_flags(int* flags) {
     return VPDQ_B200_OK;
 }
 
+int fused2_timeout_flag_async(int* h_flag, cudaStream_t stream) {
+    VPDQ_CUDA(cudaMemcpyFromSymbolAsync(h_flag, g_fused2_timeout, sizeof(int), 0, cudaMemcpyDeviceToHost, stream));
+    return VPDQ_B200_OK;
+}
+int fused2_force_timeout(int value) {
+    VPDQ_CUDA(cudaMemcpyToSymbol(g_fused2_timeout, &value, sizeof value));
+    return VPDQ_B200_OK;
+}
+
 // RGB24 (channels = 3) or 8-bit gray (channels = 1) frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane
 int fused2_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream) {
     CUtensorMap tmap;

@@ -501,6 +501,20 @@ int pdq_set_impl(int impl) {
     return VPDQ_B200_OK;
 }
 
+int pdq_timeout_flags_async(int* h_flags, cudaStream_t stream) {
+    int rc = systolic_timeout_flag_async(h_flags + 0, stream);
+    if (rc == 0) rc = fused2_timeout_flag_async(h_flags + 1, stream);
+    if (rc == 0) rc = fused_timeout_flag_async(h_flags + 2, stream);
+    return rc;
+}
+
+int pdq_force_timeout_flags(int value) {
+    int rc = systolic_debug_force_timeout(value);
+    if (rc == 0) rc = fused2_force_timeout(value);
+    if (rc == 0) rc = fused_force_timeout(value);
+    return rc;
+}
+
 int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t* d_hashes, int32_t* d_quality,
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (n_frames == 0) return VPDQ_B200_OK;

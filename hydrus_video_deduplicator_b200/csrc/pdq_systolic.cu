@@ -13,6 +13,7 @@
 //
 // Same arithmetic, same order, bit-identical results as the oracle (and as the tiled kernels it replaces).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -77,9 +78,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 }  // namespace
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
 template <int CH>  // 3: RGB24 frames, 1: 8-bit gray frames (== R = G = B)
 __global__ void __launch_bounds__(kSysThreads, 1)
-    kx_systolic_jarosz(const __grid_constant__ CUtensorMap tmap, long long n_frames_total, float* __restrict__ a64) {
+    kx_systolic_jarosz(const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, int use3d,
+                       long long n_frames_total, float* __restrict__ a64) {
     using R = Raw<CH>;
     extern __shared__ __align__(128) uint8_t smem_sys[];
     SysSmem<CH>& sm = *reinterpret_cast<SysSmem<CH>*>(smem_sys);
@@ -105,9 +114,13 @@ __global__ void __launch_bounds__(kSysThreads, 1)
 
     const uint32_t ring = smem_u32(&sm.ring[warp][0]), zeros = smem_u32(sm.zeros);
     const uint32_t bar0 = smem_u32(&sm.bar[warp][0]);
-    const uint32_t lane_base = ring + (lane >> 2) * R::kGroupRingBytes + (lane & 3) * R::kLaneBytes;
+    const int grp = lane >> 2;
+    const uint32_t lane_base = ring + ring_group_offset<CH>(grp) + (lane & 3) * R::kLaneBytes;
+    const int lane_a = 1 - lane + kGroupLanes * grp;  // window row of step t: a = t + lane_a (see ring_row_offset)
+    const uint32_t grp0_base = ring + ring_group_offset<CH>(0);
 
-    auto issue = [&](int E) {  // lanes 0..7 each stage the box of their group
+    // generic form of an event: lanes 0..7 each stage the 4-row box of their group (2-D map), if it exists
+    auto issue_split = [&](int E) {
         bool has = false;
         int y = 0;
         uint32_t dst = 0;
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
                 if (f < F && r0 < kImageRows) {
                     has = true;
                     y = first_row + f * 512 + r0;
-                    dst = ring + box_ring_offset<CH>(lane, s0);
+                    dst = ring + box_ring_offset<CH>(lane, E);
                 }
             }
         }
@@ -131,7 +144,28 @@ __global__ void __launch_bounds__(kSysThreads, 1)
                 mbar_arrive(bar);
         }
         __syncwarp();
-        if (has) tma_load_2d(dst, &tmap, box_x<CH>(lane), y, bar);
+        if (has) tma_load_2d(dst, &tmap2, box_x<CH>(lane), y, bar);
+    };
+    // (f, r0) of group 0's box of the next event to issue in the loop; in the common case (all eight boxes inside one
+    // frame) the event is ONE 3-D box
+    int ev_f = 0, ev_r = kBoxRows * first_loop_event();
+    auto issue = [&](int E) {
+        if (use3d && event_is_one_box(ev_f, ev_r, F)) {
+            if (lane == 0) {
+                const uint32_t bar = bar0 + 8 * (E & 1);
+                mbar_expect_tx(bar, kGroups * R::kBoxBytes);
+                tma_load_3d(ring + (E & 3) * (kGroups * R::kBoxBytes), &tmap3, 0,
+                            first_row + ev_f * 512 + ev_r - View3<CH>::kBackRows, 0, bar);
+            }
+            __syncwarp();
+        } else {
+            issue_split(E);
+        }
+        ev_r += kBoxRows;
+        if (ev_r == kStepsPerFrame) {
+            ev_r = 0;
+            ++ev_f;
+        }
     };
     auto wait = [&](int E) { mbar_wait(bar0 + 8 * (E & 1), (uint32_t)((E >> 1) & 1)); };
 
@@ -140,12 +174,13 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     // stream position of lane 0 TWO steps ahead (lane 31 prepares that row's prologue pixels one luma stage early)
     int f0n = -1, r0n = kStepsPerFrame + kFirstStep + 2;
 
-    for (int E = 0; E < first_loop_event(); ++E) issue(E);
+    for (int E = 0; E < first_loop_event(); ++E) issue_split(E);
     int issued = first_loop_event() - 1, waited = -1;
 
-    float* const out_base = a64 + (size_t)f_begin * 4096 + 2 * lane;
-    auto emit = [&](int f, int i, float v0, float v1) {
-        *reinterpret_cast<float2*>(out_base + (size_t)f * 4096 + i * 64) = make_float2(v0, v1);
+    float* optr = a64 + (size_t)f_begin * 4096 + 2 * lane;  // decimated rows are emitted in order
+    auto emit = [&](float v0, float v1) {
+        *reinterpret_cast<float2*>(optr) = make_float2(v0, v1);
+        optr += 64;
     };
 
     auto step = [&](int t, auto jtag) {
@@ -162,9 +197,10 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         // the raw window of the NEXT step's row (its lumas are this step's filler work)
         uint32_t w[R::kWords];
         {
-            const uint32_t off = L.next_reads_image(F) ? lane_base + ((t + 1 - lane) & (kRing - 1)) * R::kSegPitch : zeros;
+            const int a = t + lane_a;
+            const uint32_t off = L.img_next ? lane_base + (a & 12) * (kGroups * R::kBoxBytes / 4) + (a & 3) * R::kSegPitch : zeros;
             const bool nimg = (unsigned)f0n < (unsigned)F && r0n < kImageRows;
-            const uint32_t last31 = nimg ? ring + ((t + 2) & (kRing - 1)) * R::kSegPitch : zeros;
+            const uint32_t last31 = nimg ? grp0_base + ring_row_offset<CH>(0, t + 2) : zeros;
             const uint32_t last = lane == 31 ? last31 : off + 16 * (R::kChunks - 1);
 #pragma unroll
             for (int q = 0; q < R::kChunks - 1; ++q) {
@@ -242,6 +278,32 @@ int systolic_timeout_flag_async(int* h_flag, cudaStream_t stream) {
     return VPDQ_B200_OK;
 }
 
+// The 3-D view that turns the eight time-shifted group boxes of an event into ONE box (pdq_systolic_core.h View3):
+// element (x, y, g') = byte kBase3 + x + row_bytes * y + kStride3 * g' of the frame buffer.  The views of different
+// g' overlap in memory on purpose; only boxes that lie inside the buffer are ever requested.
+static int systolic_make_tensor_map3(const uint8_t* d_frames, int64_t n_frames, int channels, CUtensorMap* tmap) {
+    EncodeTiledFn encode = sys_get_encode();
+    if (!encode) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return VPDQ_B200_ERR_CUDA;
+    }
+    const int pitch = channels == 3 ? Raw<3>::kSegPitch : Raw<1>::kSegPitch;
+    const long long stride3 = channels == 3 ? View3<3>::kStride3 : View3<1>::kStride3;
+    const long long base3 = channels == 3 ? View3<3>::kBase3 : View3<1>::kBase3;
+    const cuuint64_t gdim[3] = {(cuuint64_t)pitch, (cuuint64_t)n_frames * 512, (cuuint64_t)kGroups};
+    const cuuint64_t gstride[2] = {(cuuint64_t)512 * channels, (cuuint64_t)stride3};
+    const cuuint32_t box[3] = {(cuuint32_t)pitch, (cuuint32_t)kBoxRows, (cuuint32_t)kGroups};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_frames) + base3, gdim, gstride,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3-D view) failed with CUresult %d", (int)r);
+        return VPDQ_B200_ERR_CUDA;
+    }
+    return VPDQ_B200_OK;
+}
+
 // the batch seen as [n * 512 rows][512 * channels bytes]; box = 4 rows x one lane group's share (+ overlap)
 static int systolic_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, int channels, CUtensorMap* tmap) {
     EncodeTiledFn encode = sys_get_encode();
@@ -269,8 +331,15 @@ int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_fram
         set_error("pdq: at most %d frames per launch", 0x7fffffff / 512 - 8);
         return VPDQ_B200_ERR_INVALID;
     }
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap3;
     int rc = systolic_make_tensor_map(d_frames, n_frames, channels, &tmap);
+    if (rc) return rc;
+    // (VPDQ_B200_SYSTOLIC_3D=0: every event as eight 2-D boxes -- for A/B runs)
+    static const int use3d = [] {
+        const char* e = getenv("VPDQ_B200_SYSTOLIC_3D");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    rc = use3d ? systolic_make_tensor_map3(d_frames, n_frames, channels, &tmap3) : systolic_make_tensor_map(d_frames, n_frames, channels, &tmap3);
     if (rc) return rc;
     int dev = 0, sms = 148;
     VPDQ_CUDA(cudaGetDevice(&dev));
@@ -290,9 +359,9 @@ int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_fram
     // persistent: one CTA per SM; fewer when the batch has fewer frames than the grid has warps
     const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);
     if (channels == 3)
-        kx_systolic_jarosz<3><<<grid, kSysThreads, sizeof(SysSmem<3>), stream>>>(tmap, (long long)n_frames, d_a64);
+        kx_systolic_jarosz<3><<<grid, kSysThreads, sizeof(SysSmem<3>), stream>>>(tmap, tmap3, use3d, (long long)n_frames, d_a64);
     else
-        kx_systolic_jarosz<1><<<grid, kSysThreads, sizeof(SysSmem<1>), stream>>>(tmap, (long long)n_frames, d_a64);
+        kx_systolic_jarosz<1><<<grid, kSysThreads, sizeof(SysSmem<1>), stream>>>(tmap, tmap3, use3d, (long long)n_frames, d_a64);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

@@ -147,17 +147,42 @@ struct Raw {
 };
 
 // ---- stream bookkeeping ----------------------------------------------------------------------------------
+// Ring layout per warp: [4 box slots][8 groups, stored in REVERSE order g' = 7 - g][4 rows][kSegPitch bytes].  The
+// box of event E of EVERY group sits in box slot E & 3 (group g's rows of event E are stream rows 4 E - 4 g .. + 3),
+// so that in the common case ONE 3-D TMA box (x, row, g') fills a whole slot; stream row s of group g is in box slot
+// ((s >> 2) + g) & 3, row s & 3.
+template <int CH>
+VPDQS_HD int ring_group_offset(int g) { return (kGroups - 1 - g) * Raw<CH>::kBoxBytes; }
+template <int CH>
+VPDQS_HD int ring_row_offset(int g, int s) {
+    const int a = s + kGroupLanes * g;
+    return ((a >> 2) & 3) * (kGroups * Raw<CH>::kBoxBytes) + (a & 3) * Raw<CH>::kSegPitch;
+}
 // byte offset (inside the warp's ring) of the window of `lane` for stream row s
 template <int CH>
 VPDQS_HD int ring_offset(int lane, int s) {
-    return (lane >> 2) * Raw<CH>::kGroupRingBytes + (s & (kRing - 1)) * Raw<CH>::kSegPitch + (lane & 3) * Raw<CH>::kLaneBytes;
+    return ring_row_offset<CH>(lane >> 2, s) + ring_group_offset<CH>(lane >> 2) + (lane & 3) * Raw<CH>::kLaneBytes;
 }
 // the TMA box of event E for group g: first stream row (may be negative = nothing to load)
 VPDQS_HD int box_first_row(int E, int g) { return kBoxRows * E - kGroupLanes * g; }
 template <int CH>
-VPDQS_HD int box_ring_offset(int g, int s0) { return g * Raw<CH>::kGroupRingBytes + (s0 & (kRing - 1)) * Raw<CH>::kSegPitch; }
+VPDQS_HD int box_ring_offset(int g, int E) { return (E & 3) * (kGroups * Raw<CH>::kBoxBytes) + ring_group_offset<CH>(g); }
 template <int CH>
 VPDQS_HD int box_x(int g) { return g * Raw<CH>::kSegBytes; }
+// The 3-D view of the batch that makes all 8 boxes of an event one TMA box: element (x, y, g') lives at byte
+//   kBase3 + x + kRowBytes * y + kStride3 * g'   of the frame buffer,   g' = 7 - g,
+// i.e. group g's share (byte 192 g .. of the row) of image row  y + 28 - 4 g.  An event whose group-0 box starts at
+// image row r0 of a frame (global row Y0) is the box at (0, Y0 - 28, 0) of size (kSegPitch, 4, 8) -- valid when all
+// eight boxes lie in that one frame: 28 <= r0 <= 508.
+template <int CH>
+struct View3 {
+    static constexpr int kBackRows = kGroupLanes * (kGroups - 1);                                   // 28
+    static constexpr long long kStride3 = (long long)kGroupLanes * Raw<CH>::kRowBytes - Raw<CH>::kSegBytes;  // 5952 / 1984
+    static constexpr long long kBase3 = (long long)(kGroups - 1) * Raw<CH>::kSegBytes;              // 1344 / 448
+};
+VPDQS_HD bool event_is_one_box(int f, int r0, int n_frames) {
+    return f < n_frames && r0 >= kGroupLanes * (kGroups - 1) && r0 <= kImageRows - kBoxRows;
+}
 // last step of a warp that owns F frames: lane 31 at stream row 516 (F - 1) + 513 (P3 / P4 run one step behind P2,
 // whose last output row 510 appears at row 512)
 VPDQS_HD int last_step(int F) { return kStepsPerFrame * (F - 1) + kImageRows + 1 + 31; }
@@ -185,6 +210,9 @@ struct LaneState {
     F2 h4[4];
     RowChain in1, in3;     // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
     int r, f;              // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
+    // predicates that only change in the rare-row tail (so that the common path evaluates no row comparisons):
+    bool img_next;         // the NEXT step's row is an image row of one of the warp's frames (its window is staged)
+    bool zvalid;           // this step's P3 row (P2 output row r - 3) is real: 3 <= r <= 513 of a live frame
     VPDQS_HD void init(int lane) {
         VPDQS_UNROLL
         for (int p = 0; p < kCols / 2; ++p) {
@@ -200,12 +228,8 @@ struct LaneState {
         // stream row of lane l at the first step = kFirstStep - l < 0: rows of the virtual frame -1 (never live)
         f = -1;
         r = kStepsPerFrame + kFirstStep - lane;
-    }
-    // does the NEXT step of this lane read an image row?
-    VPDQS_HD bool next_reads_image(int n_frames) const {
-        const bool wrap = r + 1 == kStepsPerFrame;
-        const int rn = wrap ? 0 : r + 1, fn = wrap ? f + 1 : f;
-        return (unsigned)fn < (unsigned)n_frames && rn < kImageRows;
+        img_next = false;
+        zvalid = false;
     }
 };
 
@@ -232,15 +256,15 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
 }
 
 // One lane, one step.  J = step & 3 (history slot).  w = the raw window of the lane's NEXT stream row (zeros when
-// that row is not an image row); for lane 31 the LAST chunk is instead the first 16 bytes of the row lane 0 works
-// on TWO steps ahead (zeros if that is not an image row).
+// that row is not an image row: L.img_next); for lane 31 the LAST chunk is instead the first 16 bytes of the row
+// lane 0 works on TWO steps ahead (zeros if that is not an image row).
 //
-// The step has one branch-free main block in which the two serial chains -- P1 over this step's row r and P3 over
+// The step is one branch-free main block in which the two serial chains -- P1 over this step's row r and P3 over
 // the P2 outputs of the PREVIOUS step (output row r - 3) -- start with every input ready and run side by side with
-// the independent work (P2, and the lumas of the NEXT step's row) that fills their latency, and a tail with the
-// rare per-lane cases (divisor-3 rows, frame start).
+// the independent work (P2, and the lumas of the NEXT step's row) that fills their latency, followed by ONE branch
+// into the tail for the rare rows (divisor-3 rows, the frame boundary).
 // out1 / out3: the chain states to hand to lane l + 1 (lane 31 -> lane 0: the next row's initial states).
-// emit(frame, i, v0, v1): decimated row i of columns 2l, 2l+1 is final.
+// emit(v0, v1): the next decimated row (in order: rows 0..63 of frame 0, 1, ...) of columns 2l, 2l+1 is final.
 template <int CH, int J, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
@@ -250,16 +274,17 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
     float z0 = 0.0f, z1 = 0.0f;
     // lane 31: its last two lumas are the NEXT row's pixels 0, 1 (its own row has only the drain zeros left there)
     const float xa = L.x[7].x, xb = L.x[7].y;
+    const bool first = lane == 0, last = lane == 31;
     VPDQS_UNROLL
     for (int p = 0; p < kCols / 2; ++p) {
         const int k = 2 * p;
         xn[p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
         F2 x = L.x[p];
-        if (p == 7 && lane == 31) x = f2_splat(0.0f);
+        if (p == 7) x = F2{last ? 0.0f : x.x, last ? 0.0f : x.y};
         // P1: row pass 1 along the lanes -> output columns 16 l + k, + 1 (unscaled, x4)
         float v0 = row_feed(c1, x.x);
-        if (p == 0 && lane == 0) v0 = edge3(v0);   // column 0: divisor 3
-        if (p == 7 && lane == 31) v0 = edge3(v0);  // column 510: divisor 3 (column 511 feeds no decimated output)
+        if (p == 0) v0 = first ? edge3(v0) : v0;  // column 0: divisor 3
+        if (p == 7) v0 = last ? edge3(v0) : v0;   // column 510: divisor 3 (column 511 feeds no decimated output)
         const float v1 = row_feed(c1, x.y);
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
@@ -275,50 +300,56 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         if (k == 14) z1 = u0;
         row_feed(c3, prev.y);
     }
-    // P4: column pass 2, private, fed P3 row r - 3 (real for 3 <= r <= 513, zeros otherwise) -> output row r - 5
+    // P4: column pass 2, private, fed P3 row r - 3 (zeros unless zvalid) -> output row r - 5
     {
-        const bool zvalid = r >= 3 && r <= kImageRows + 1;
-        const F2 z = zvalid ? F2{z0, z1} : f2_splat(0.0f);
+        const F2 z{L.zvalid ? z0 : 0.0f, L.zvalid ? z1 : 0.0f};
         const F2 old = L.h4[J];
         F2 s = f2_add(L.s4, z);
         s = f2_sub(s, old);
         L.h4[J] = z;
         L.s4 = s;
-        if ((unsigned)L.f < (unsigned)n_frames && r >= 9 && (r & 7) == 1)  // output row r - 5 = 8 i + 4
-            emit(L.f, ((r - 1) >> 3) - 1, fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
+        if (L.zvalid && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
+            emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
     }
-    // hand-over
-    out1 = c1;
-    out3 = c3;
-    if (lane == 31) {  // -> lane 0, next row: the chain after the prologue pixels 0, 1 (fed without output) / a fresh chain
-        out1 = RowChain{fadd(xa, xb), 0.0f, 0.0f, xa, xb};
-        out3 = row_zero();
-    }
-    // ---- tail: the rare per-lane cases ----
-    // P2 output rows 0 (r = 2) and 510 (r = 512) have divisor 3.  The sums double as P3's input of the next step, so
-    // the fix-up is done IN PLACE (no second set of registers, no copies in the common path): after row 510 the sums
-    // are dead anyway (zero rows follow, reset at the frame start); after row 0 the next step's P2 update runs on the
-    // fixed-up value and is wrong for this lane -- its tail (r = 3) rebuilds the sums from the history, which at that
-    // point holds exactly rows 0..3: ((v0 + v1) + v2) + v3, the very operations of the running sum (its
-    // subtractions are all of zeros there).
-    if (r == 2 || r == kImageRows) {
-        VPDQS_UNROLL
-        for (int p = 0; p < kCols / 2; ++p) L.s2[p] = F2{edge3(L.s2[p].x), edge3(L.s2[p].y)};
-        // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
-        if (r == 2) L.s4 = f2_splat(0.0f);
-    }
-    if (r == 3) {
-        VPDQS_UNROLL
-        for (int p = 0; p < kCols / 2; ++p)
-            L.s2[p] = f2_add(f2_add(f2_add(L.h2[(J + 1) & 3][p], L.h2[(J + 2) & 3][p]), L.h2[(J + 3) & 3][p]), L.h2[J][p]);
-    }
+    // hand-over (lane 31 -> lane 0, next row: the chain after the prologue pixels 0, 1, fed without output / a fresh chain)
+    out1 = RowChain{last ? fadd(xa, xb) : c1.s, last ? 0.0f : c1.h0, last ? 0.0f : c1.h1, last ? xa : c1.h2,
+                    last ? xb : c1.h3};
+    out3 = RowChain{last ? 0.0f : c3.s, last ? 0.0f : c3.h0, last ? 0.0f : c3.h1, last ? 0.0f : c3.h2,
+                    last ? 0.0f : c3.h3};
     VPDQS_UNROLL
     for (int p = 0; p < kCols / 2; ++p) L.x[p] = xn[p];
-    if (++L.r == kStepsPerFrame) {  // next step starts a new frame: the P2 histories were flushed by the four zero
-        L.r = 0;                    // rows, the sums hold rounding residue
-        ++L.f;
-        VPDQS_UNROLL
-        for (int p = 0; p < kCols / 2; ++p) L.s2[p] = f2_splat(0.0f);
+    L.r = r + 1;
+    // ---- tail: the rare rows ----
+    if ((unsigned)(r - 2) < 2u || r >= kImageRows - 2) {
+        const bool live = (unsigned)L.f < (unsigned)n_frames;
+        // P2 output rows 0 (r = 2) and 510 (r = 512) have divisor 3.  The sums double as P3's input of the next step,
+        // so the fix-up is done IN PLACE (no second set of registers, no copies in the common path): after row 510
+        // the sums are dead anyway (zero rows follow, reset at the frame start); after row 0 the next step's P2
+        // update runs on the fixed-up value and is wrong for this lane -- its tail (r = 3) rebuilds the sums from the
+        // history, which at that point holds exactly rows 0..3: ((v0 + v1) + v2) + v3, the very operations of the
+        // running sum (its subtractions are all of zeros there).
+        if (r == 2 || r == kImageRows) {
+            VPDQS_UNROLL
+            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = F2{edge3(L.s2[p].x), edge3(L.s2[p].y)};
+        }
+        if (r == 2) {  // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
+            L.s4 = f2_splat(0.0f);
+            L.zvalid = live;
+        }
+        if (r == 3) {
+            VPDQS_UNROLL
+            for (int p = 0; p < kCols / 2; ++p)
+                L.s2[p] = f2_add(f2_add(f2_add(L.h2[(J + 1) & 3][p], L.h2[(J + 2) & 3][p]), L.h2[(J + 3) & 3][p]), L.h2[J][p]);
+        }
+        if (r == kImageRows - 2) L.img_next = false;     // the step after next reads row 512: not an image row
+        if (r == kImageRows + 1) L.zvalid = false;       // P2 output row 510 was the last real one
+        if (r == kStepsPerFrame - 2) L.img_next = (unsigned)(L.f + 1) < (unsigned)n_frames;  // row 0 of the next frame
+        if (r == kStepsPerFrame - 1) {  // next step starts a new frame: the P2 histories were flushed by the four zero
+            L.r = 0;                    // rows, the sums hold rounding residue
+            ++L.f;
+            VPDQS_UNROLL
+            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = f2_splat(0.0f);
+        }
     }
 }
 

@@ -21,24 +21,57 @@ template <int CH>
 struct WarpSim {
     using R = Raw<CH>;
     uint8_t ring[R::kWarpRingBytes];
-    int slot_row[kGroups][kRing];   // stream row held by each ring slot, or INT_MIN while a copy is in flight / never loaded
+    int slot_row[kGroups][kRing];   // stream row held by each ring row of a group, or a sentinel while a copy is in flight
     struct Pending {
-        int E, g, s0;
+        int E, off, bytes;
         std::vector<uint8_t> data;
+        std::vector<int> g, s0;     // which (group, first stream row) boxes it carries
     };
     std::vector<Pending> pending;
     const uint8_t* frames;
     long long total_rows, first_row;  // of the whole batch / of this warp's first frame
     int F;
     int errors = 0;
+    int one_box_events = 0, split_events = 0;
 
+    static int row_index(int g, int s) { return (((s + kGroupLanes * g) >> 2) & 3) * 4 + (s & 3); }
+    void invalidate(int g, int s0) {
+        for (int i = 0; i < kBoxRows; ++i) slot_row[g][row_index(g, s0 + i)] = -2000000000;
+    }
     void issue(int E) {
+        const int s00 = box_first_row(E, 0);
+        const int f0 = s00 / kStepsPerFrame, r00 = s00 % kStepsPerFrame;
+        if (s00 >= 0 && event_is_one_box(f0, r00, F)) {
+            // ONE 3-D box (x, row, g') at (0, Y0 - 28, 0): element address = kBase3 + x + kRowBytes*y + kStride3*g'
+            ++one_box_events;
+            Pending p{E, box_ring_offset<CH>(kGroups - 1, E), kGroups * R::kBoxBytes, std::vector<uint8_t>(kGroups * R::kBoxBytes), {}, {}};
+            const long long y0 = first_row + (long long)f0 * 512 + r00 - View3<CH>::kBackRows;
+            for (int gp = 0; gp < kGroups; ++gp)
+                for (int i = 0; i < kBoxRows; ++i)
+                    for (int x = 0; x < R::kSegPitch; ++x) {
+                        const long long addr = View3<CH>::kBase3 + x + (long long)R::kRowBytes * (y0 + i) + View3<CH>::kStride3 * gp;
+                        if (addr < 0 || addr >= total_rows * R::kRowBytes) {  // the one-box path must never leave the buffer
+                            ++errors;
+                            continue;
+                        }
+                        p.data[(gp * kBoxRows + i) * R::kSegPitch + x] = frames[addr];
+                    }
+            for (int g = 0; g < kGroups; ++g) {
+                p.g.push_back(g);
+                p.s0.push_back(box_first_row(E, g));
+                invalidate(g, box_first_row(E, g));
+            }
+            memset(ring + p.off, 0xCD, p.bytes);
+            pending.push_back(std::move(p));
+            return;
+        }
+        ++split_events;
         for (int g = 0; g < kGroups; ++g) {
             const int s0 = box_first_row(E, g);
             if (s0 < 0) continue;
             const int f = s0 / kStepsPerFrame, r0 = s0 % kStepsPerFrame;
             if (f >= F || r0 >= kImageRows) continue;
-            Pending p{E, g, s0, std::vector<uint8_t>(R::kBoxBytes)};
+            Pending p{E, box_ring_offset<CH>(g, E), R::kBoxBytes, std::vector<uint8_t>(R::kBoxBytes), {g}, {s0}};
             for (int i = 0; i < kBoxRows; ++i)
                 for (int b = 0; b < R::kSegPitch; ++b) {
                     const long long row = first_row + (long long)f * 512 + r0 + i;
@@ -46,9 +79,8 @@ struct WarpSim {
                     p.data[i * R::kSegPitch + b] =
                         (row >= 0 && row < total_rows && col < R::kRowBytes) ? frames[row * R::kRowBytes + col] : 0;
                 }
-            const int off = box_ring_offset<CH>(g, s0);
-            memset(ring + off, 0xCD, R::kBoxBytes);
-            for (int i = 0; i < kBoxRows; ++i) slot_row[g][(s0 + i) & (kRing - 1)] = -2000000000;
+            memset(ring + p.off, 0xCD, p.bytes);
+            invalidate(g, s0);
             pending.push_back(std::move(p));
         }
     }
@@ -56,8 +88,9 @@ struct WarpSim {
         for (size_t i = 0; i < pending.size();) {
             if (pending[i].E == E) {
                 const Pending& p = pending[i];
-                memcpy(ring + box_ring_offset<CH>(p.g, p.s0), p.data.data(), R::kBoxBytes);
-                for (int k = 0; k < kBoxRows; ++k) slot_row[p.g][(p.s0 + k) & (kRing - 1)] = p.s0 + k;
+                memcpy(ring + p.off, p.data.data(), p.bytes);
+                for (size_t b = 0; b < p.g.size(); ++b)
+                    for (int k = 0; k < kBoxRows; ++k) slot_row[p.g[b]][row_index(p.g[b], p.s0[b] + k)] = p.s0[b] + k;
                 pending.erase(pending.begin() + i);
             } else {
                 ++i;
@@ -68,13 +101,13 @@ struct WarpSim {
     void read_chunk(int lane, int s, int q, uint32_t* dst) {
         const int g = lane >> 2;
         // a window's last chunk may reach into the next group's share of the row: still this group's box
-        if (slot_row[g][s & (kRing - 1)] != s) ++errors;
+        if (slot_row[g][row_index(g, s)] != s) ++errors;
         memcpy(dst, ring + ring_offset<CH>(lane, s) + 16 * q, 16);
     }
 };
 
 template <int CH, int J>
-void step_all(WarpSim<CH>& W, LaneState* st, int t, float* a64, long long f_first) {
+void step_all(WarpSim<CH>& W, LaneState* st, float** optr, int t) {
     using R = Raw<CH>;
     RowChain out1[32], out3[32];
     const int next0 = t + 2;  // stream row of lane 0 two steps ahead (lane 31 prepares its prologue pixels)
@@ -82,16 +115,16 @@ void step_all(WarpSim<CH>& W, LaneState* st, int t, float* a64, long long f_firs
     for (int lane = 0; lane < 32; ++lane) {
         uint32_t w[R::kWords];
         memset(w, 0, sizeof w);
-        if (st[lane].next_reads_image(W.F)) {  // the window of the NEXT step's row
-            const int s = t + 1 - lane;
-            if (s != st[lane].f * kStepsPerFrame + st[lane].r + 1) ++W.errors;
+        const int s = t + 1 - lane;  // the NEXT step's row of this lane
+        const bool want = s >= 0 && s / kStepsPerFrame < W.F && s % kStepsPerFrame < kImageRows;
+        if (want != st[lane].img_next) ++W.errors;  // the loop-carried predicate must agree with the stream position
+        if (st[lane].img_next)
             for (int q = 0; q < R::kChunks - (lane == 31 ? 1 : 0); ++q) W.read_chunk(lane, s, q, w + 4 * q);
-        }
         if (lane == 31 && next0_image) W.read_chunk(0, next0, 0, w + 4 * (R::kChunks - 1));
-        lane_step<CH, J>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](int f, int i, float v0, float v1) {
-            float* o = a64 + (size_t)(f_first + f) * 4096 + i * 64 + 2 * lane;
-            o[0] = v0;
-            o[1] = v1;
+        lane_step<CH, J>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](float v0, float v1) {
+            optr[lane][0] = v0;
+            optr[lane][1] = v1;
+            optr[lane] += 64;
         });
     }
     for (int lane = 0; lane < 32; ++lane) {
@@ -116,7 +149,11 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
         W->first_row = f_begin * 512;
         W->F = F;
         LaneState st[32];
-        for (int l = 0; l < 32; ++l) st[l].init(l);
+        float* optr[32];
+        for (int l = 0; l < 32; ++l) {
+            st[l].init(l);
+            optr[l] = a64 + (size_t)f_begin * 4096 + 2 * l;
+        }
         for (int E = 0; E < first_loop_event(); ++E) W->issue(E);
         int issued = first_loop_event() - 1, waited = -1;
         const int t_last = last_step(F);
@@ -128,14 +165,17 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 issued = Ei;
             }
             switch (t & 3) {
-                case 0: step_all<CH, 0>(*W, st, t, a64, f_begin); break;
-                case 1: step_all<CH, 1>(*W, st, t, a64, f_begin); break;
-                case 2: step_all<CH, 2>(*W, st, t, a64, f_begin); break;
-                default: step_all<CH, 3>(*W, st, t, a64, f_begin); break;
+                case 0: step_all<CH, 0>(*W, st, optr, t); break;
+                case 1: step_all<CH, 1>(*W, st, optr, t); break;
+                case 2: step_all<CH, 2>(*W, st, optr, t); break;
+                default: step_all<CH, 3>(*W, st, optr, t); break;
             }
         }
         for (int E = waited + 1; E <= issued; ++E) W->wait(E);
         if (!W->pending.empty()) ++errors;
+        for (int l = 0; l < 32; ++l)
+            if (optr[l] != a64 + (size_t)(f_begin + F) * 4096 + 2 * l) ++errors;  // every decimated row was emitted, in order
+        if (F > 1 && W->one_box_events < 100 * F) ++errors;  // the one-box path must be the common one
         errors += W->errors;
         delete W;
     }
