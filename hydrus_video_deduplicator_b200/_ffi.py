@@ -49,6 +49,7 @@ PROTOTYPES = {
     "vpdq_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "vpdq_b200_kernel_launches": (C.c_int, [C.POINTER(C.c_uint64)]),
     "vpdq_b200_debug_flags": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "vpdq_b200_debug_force_timeout": (C.c_int, [C.c_int, C.c_int]),
     "vpdq_b200_set_pdq_impl": (C.c_int, [C.c_int]),
     "vpdq_b200_get_pdq_impl": (C.c_int, []),
     "vpdq_b200_dct_matrix": (C.c_int, [_f32p]),
@@ -62,6 +63,8 @@ PROTOTYPES = {
     "vpdq_b200_pdq_hash_frames_host": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "vpdq_b200_hasher_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "vpdq_b200_hasher_push": (C.c_int, [_vp, _vp, C.c_int64]),
+    "vpdq_b200_hasher_push_nocopy": (C.c_int, [_vp, _vp, C.c_int64]),
+    "vpdq_b200_hasher_consumed": (C.c_int, [_vp, _i64p]),
     "vpdq_b200_hasher_pushed": (C.c_int, [_vp, _i64p]),
     "vpdq_b200_hasher_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _i64p, _vp, _vp]),
     "vpdq_b200_hasher_destroy": (C.c_int, [_vp]),

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     };
 
     auto step = [&](int t, auto jtag) {
-        constexpr int J = decltype(jtag)::value;
-        if (J == kEventPhase) {
+        constexpr int T8 = decltype(jtag)::value;
+        if ((T8 & 3) == kEventPhase) {
             const int Ew = (t + kWaitLead) >> 2, Ei = (t + kIssueLead) >> 2;
             if (Ew >= 0) {
                 wait(Ew);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
             w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
         RowChain o1, o3;
-        lane_step<CH, J>(L, w, lane, F, o1, o3, emit);
+        lane_step<CH, T8>(L, w, lane, F, o1, o3, emit);
         const int src = (lane + 31) & 31;
         L.in1.s = __shfl_sync(0xffffffffu, o1.s, src);
         L.in1.h0 = __shfl_sync(0xffffffffu, o1.h0, src);
@@ -232,11 +232,15 @@ __global__ void __launch_bounds__(kSysThreads, 1)
 
     const int t_last = last_step(F);
 #pragma unroll 1
-    for (int t = kFirstStep; t <= t_last; t += 4) {  // (steps past t_last only see rows that are not live)
+    for (int t = kFirstStep; t <= t_last; t += 8) {  // (steps past t_last only see rows that are not live)
         step(t, std::integral_constant<int, 0>{});
         step(t + 1, std::integral_constant<int, 1>{});
         step(t + 2, std::integral_constant<int, 2>{});
         step(t + 3, std::integral_constant<int, 3>{});
+        step(t + 4, std::integral_constant<int, 4>{});
+        step(t + 5, std::integral_constant<int, 5>{});
+        step(t + 6, std::integral_constant<int, 6>{});
+        step(t + 7, std::integral_constant<int, 7>{});
     }
     for (int E = waited + 1; E <= issued; ++E) wait(E);  // no copy may be in flight when the CTA retires
 }

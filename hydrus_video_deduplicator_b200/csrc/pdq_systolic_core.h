@@ -105,6 +105,27 @@ VPDQS_HD F2 f2_sub(F2 a, F2 b) { return F2{fsub(a.x, b.x), fsub(a.y, b.y)}; }
 VPDQS_HD F2 f2_fma(F2 a, F2 b, F2 c) { return F2{ffma(a.x, b.x, c.x), ffma(a.y, b.y, c.y)}; }
 #endif
 VPDQS_HD F2 f2_splat(float v) { return F2{v, v}; }
+VPDQS_HD F2 f2_mul(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+    const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return F2{r.x, r.y};
+#else
+    return F2{fmul(a.x, b.x), fmul(a.y, b.y)};
+#endif
+}
+
+// branch-free selects on the bit patterns (one LOP3 each): m = all ones -> a, m = 0 -> b
+VPDQS_HD uint32_t float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+VPDQS_HD float bitsel(uint32_t m, float a, float b) { return bits_to_float((float_bits(a) & m) | (float_bits(b) & ~m)); }
+VPDQS_HD float bitkeep(uint32_t m, float a) { return bits_to_float(float_bits(a) & m); }  // m ? a : +0
 
 // v / 3.0f, correctly rounded, branch free (Markstein; equal to IEEE division for every finite positive float,
 // tests/emu/div3_check.c), and invariant under power-of-two scaling of v
@@ -116,6 +137,12 @@ VPDQS_HD float div3(float v) {
 }
 // a divisor-3 output in the deferred-scale representation
 VPDQS_HD float edge3(float v) { return fmul(div3(v), 4.0f); }
+VPDQS_HD F2 edge3(F2 v) {  // the same on a packed pair (no multiply feeds an add here: nothing for ptxas to contract)
+    const F2 c = f2_splat(0.333333343267440796f);
+    const F2 q = f2_mul(v, c);
+    const F2 r = f2_fma(f2_splat(-3.0f), q, v);
+    return f2_mul(f2_fma(r, c, q), f2_splat(4.0f));
+}
 
 constexpr int kCols = 16;            // image columns per lane
 constexpr int kStepsPerFrame = 516;  // 512 image rows + 4 zero rows
@@ -124,7 +151,7 @@ constexpr int kRing = 16;            // stream rows per group ring
 constexpr int kBoxRows = 4;          // stream rows per TMA box
 constexpr int kGroupLanes = 4;
 constexpr int kGroups = 32 / kGroupLanes;  // 8
-constexpr int kFirstStep = -4;       // the step loop starts here (a multiple of 4; steps < 0 only prepare lane 0's first row)
+constexpr int kFirstStep = -8;       // the step loop starts here (a multiple of 8; steps < 0 only prepare lane 0's first row)
 constexpr int kIssueLead = 10;       // ISSUE(E) at step 4 E - 10
 constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
                                      // computed one step ahead, as filler work for the serial chains)
@@ -200,38 +227,45 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
     return c.s;
 }
 
+// The step loop is unrolled by 8: T8 = step & 7 selects the history slot (T8 & 3) and which of two register sets a
+// value is read from / written to, so that a new value is computed straight into its final register while the old
+// one is still being consumed (no register copies): the lumas alternate every step, the histories every 4 steps.
 struct LaneState {
-    F2 s2[kCols / 2];      // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start of
-                           // a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
-                           // (one set of registers for both: see the tail of lane_step for the divisor-3 rows)
-    F2 h2[4][kCols / 2];   // P2 histories (the last four inputs), slot = step & 3
-    F2 x[kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous step
-    F2 s4;                 // P4 running sums of the two decimated columns 2l, 2l+1
-    F2 h4[4];
-    RowChain in1, in3;     // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
-    int r, f;              // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
+    F2 s2[kCols / 2];         // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start
+                              // of a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
+                              // (one set of registers for both: see the tail of lane_step for the divisor-3 rows)
+    F2 h2[2][4][kCols / 2];   // P2 histories (the last four inputs): the value written at step u is h2[set(u)][u & 3]
+    F2 x[2][kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..) in x[step & 1], computed during the previous step
+    F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
+    F2 h4[2][4];
+    RowChain in1, in3;        // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
+    int r, f;                 // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
     // predicates that only change in the rare-row tail (so that the common path evaluates no row comparisons):
-    bool img_next;         // the NEXT step's row is an image row of one of the warp's frames (its window is staged)
-    bool zvalid;           // this step's P3 row (P2 output row r - 3) is real: 3 <= r <= 513 of a live frame
+    bool img_next;            // the NEXT step's row is an image row of one of the warp's frames (its window is staged)
+    uint32_t zmask;           // all ones iff this step's P3 row (P2 output row r - 3) is real: 3 <= r <= 513 of a live frame
     VPDQS_HD void init(int lane) {
         VPDQS_UNROLL
         for (int p = 0; p < kCols / 2; ++p) {
             s2[p] = f2_splat(0.0f);
-            h2[0][p] = h2[1][p] = h2[2][p] = h2[3][p] = f2_splat(0.0f);
-            x[p] = f2_splat(0.0f);
+            VPDQS_UNROLL
+            for (int j = 0; j < 4; ++j) h2[0][j][p] = h2[1][j][p] = f2_splat(0.0f);
+            x[0][p] = x[1][p] = f2_splat(0.0f);
         }
         s4 = f2_splat(0.0f);
         VPDQS_UNROLL
-        for (int j = 0; j < 4; ++j) h4[j] = f2_splat(0.0f);
+        for (int j = 0; j < 4; ++j) h4[0][j] = h4[1][j] = f2_splat(0.0f);
         in1 = row_zero();
         in3 = row_zero();
         // stream row of lane l at the first step = kFirstStep - l < 0: rows of the virtual frame -1 (never live)
         f = -1;
         r = kStepsPerFrame + kFirstStep - lane;
         img_next = false;
-        zvalid = false;
+        zmask = 0u;
     }
 };
+// where the history value written at step u (u & 7 = U8) lives
+constexpr int hist_set(int U8) { return ((((U8 + 8) & 7) >> 2) & 1) ^ 1; }
+constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
 
 // M = 2^23 + byte: the byte at offset b of the little-endian word array spliced into the mantissa of 2^23 (PRMT)
 template <int N>
@@ -255,9 +289,9 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
     return f2_add(f2_add(r, g), b);  // (0.299 R + 0.587 G) + 0.114 B
 }
 
-// One lane, one step.  J = step & 3 (history slot).  w = the raw window of the lane's NEXT stream row (zeros when
-// that row is not an image row: L.img_next); for lane 31 the LAST chunk is instead the first 16 bytes of the row
-// lane 0 works on TWO steps ahead (zeros if that is not an image row).
+// One lane, one step.  T8 = step & 7.  w = the raw window of the lane's NEXT stream row (zeros when that row is not an
+// image row: L.img_next); for lane 31 the LAST chunk is instead the first 16 bytes of the row lane 0 works on TWO
+// steps ahead (zeros if that is not an image row).
 //
 // The step is one branch-free main block in which the two serial chains -- P1 over this step's row r and P3 over
 // the P2 outputs of the PREVIOUS step (output row r - 3) -- start with every input ready and run side by side with
@@ -265,33 +299,33 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
 // into the tail for the rare rows (divisor-3 rows, the frame boundary).
 // out1 / out3: the chain states to hand to lane l + 1 (lane 31 -> lane 0: the next row's initial states).
 // emit(v0, v1): the next decimated row (in order: rows 0..63 of frame 0, 1, ...) of columns 2l, 2l+1 is final.
-template <int CH, int J, typename Emit>
+template <int CH, int T8, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
+    constexpr int J = T8 & 3, PX = T8 & 1, PH = (T8 >> 2) & 1;
     const int r = L.r;
     RowChain c1 = L.in1, c3 = L.in3;
-    F2 xn[kCols / 2];
     float z0 = 0.0f, z1 = 0.0f;
+    const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u, first = lane == 0 ? 0xFFFFFFFFu : 0u;
     // lane 31: its last two lumas are the NEXT row's pixels 0, 1 (its own row has only the drain zeros left there)
-    const float xa = L.x[7].x, xb = L.x[7].y;
-    const bool first = lane == 0, last = lane == 31;
+    const float xa = L.x[PX][7].x, xb = L.x[PX][7].y;
     VPDQS_UNROLL
     for (int p = 0; p < kCols / 2; ++p) {
         const int k = 2 * p;
-        xn[p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
-        F2 x = L.x[p];
-        if (p == 7) x = F2{last ? 0.0f : x.x, last ? 0.0f : x.y};
+        L.x[PX ^ 1][p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
+        F2 x = L.x[PX][p];
+        if (p == 7) x = F2{bitkeep(~last, x.x), bitkeep(~last, x.y)};
         // P1: row pass 1 along the lanes -> output columns 16 l + k, + 1 (unscaled, x4)
         float v0 = row_feed(c1, x.x);
-        if (p == 0) v0 = first ? edge3(v0) : v0;  // column 0: divisor 3
-        if (p == 7) v0 = last ? edge3(v0) : v0;   // column 510: divisor 3 (column 511 feeds no decimated output)
+        if (p == 0) v0 = bitsel(first, edge3(v0), v0);  // column 0: divisor 3
+        if (p == 7) v0 = bitsel(last, edge3(v0), v0);   // column 510: divisor 3 (column 511 feeds no decimated output)
         const float v1 = row_feed(c1, x.y);
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
-        const F2 old = L.h2[J][p], prev = L.s2[p];
+        const F2 old = L.h2[PH][J][p], prev = L.s2[p];
         F2 s = f2_add(prev, v);
         s = f2_sub(s, old);
-        L.h2[J][p] = v;
+        L.h2[PH ^ 1][J][p] = v;
         L.s2[p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
@@ -300,24 +334,22 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         if (k == 14) z1 = u0;
         row_feed(c3, prev.y);
     }
-    // P4: column pass 2, private, fed P3 row r - 3 (zeros unless zvalid) -> output row r - 5
+    // P4: column pass 2, private, fed P3 row r - 3 (zeros unless real) -> output row r - 5
     {
-        const F2 z{L.zvalid ? z0 : 0.0f, L.zvalid ? z1 : 0.0f};
-        const F2 old = L.h4[J];
+        const F2 z{bitkeep(L.zmask, z0), bitkeep(L.zmask, z1)};
+        const F2 old = L.h4[PH][J];
         F2 s = f2_add(L.s4, z);
         s = f2_sub(s, old);
-        L.h4[J] = z;
+        L.h4[PH ^ 1][J] = z;
         L.s4 = s;
-        if (L.zvalid && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
+        if (L.zmask && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
             emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
     }
     // hand-over (lane 31 -> lane 0, next row: the chain after the prologue pixels 0, 1, fed without output / a fresh chain)
-    out1 = RowChain{last ? fadd(xa, xb) : c1.s, last ? 0.0f : c1.h0, last ? 0.0f : c1.h1, last ? xa : c1.h2,
-                    last ? xb : c1.h3};
-    out3 = RowChain{last ? 0.0f : c3.s, last ? 0.0f : c3.h0, last ? 0.0f : c3.h1, last ? 0.0f : c3.h2,
-                    last ? 0.0f : c3.h3};
-    VPDQS_UNROLL
-    for (int p = 0; p < kCols / 2; ++p) L.x[p] = xn[p];
+    out1 = RowChain{bitsel(last, fadd(xa, xb), c1.s), bitkeep(~last, c1.h0), bitkeep(~last, c1.h1), bitsel(last, xa, c1.h2),
+                    bitsel(last, xb, c1.h3)};
+    out3 = RowChain{bitkeep(~last, c3.s), bitkeep(~last, c3.h0), bitkeep(~last, c3.h1), bitkeep(~last, c3.h2),
+                    bitkeep(~last, c3.h3)};
     L.r = r + 1;
     // ---- tail: the rare rows ----
     if ((unsigned)(r - 2) < 2u || r >= kImageRows - 2) {
@@ -330,19 +362,22 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         // running sum (its subtractions are all of zeros there).
         if (r == 2 || r == kImageRows) {
             VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = F2{edge3(L.s2[p].x), edge3(L.s2[p].y)};
+            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = edge3(L.s2[p]);
         }
         if (r == 2) {  // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
             L.s4 = f2_splat(0.0f);
-            L.zvalid = live;
+            L.zmask = live ? 0xFFFFFFFFu : 0u;
         }
         if (r == 3) {
             VPDQS_UNROLL
             for (int p = 0; p < kCols / 2; ++p)
-                L.s2[p] = f2_add(f2_add(f2_add(L.h2[(J + 1) & 3][p], L.h2[(J + 2) & 3][p]), L.h2[(J + 3) & 3][p]), L.h2[J][p]);
+                L.s2[p] = f2_add(f2_add(f2_add(L.h2[hist_set(T8 - 3)][hist_slot(T8 - 3)][p],
+                                               L.h2[hist_set(T8 - 2)][hist_slot(T8 - 2)][p]),
+                                        L.h2[hist_set(T8 - 1)][hist_slot(T8 - 1)][p]),
+                                 L.h2[hist_set(T8)][hist_slot(T8)][p]);
         }
         if (r == kImageRows - 2) L.img_next = false;     // the step after next reads row 512: not an image row
-        if (r == kImageRows + 1) L.zvalid = false;       // P2 output row 510 was the last real one
+        if (r == kImageRows + 1) L.zmask = 0u;           // P2 output row 510 was the last real one
         if (r == kStepsPerFrame - 2) L.img_next = (unsigned)(L.f + 1) < (unsigned)n_frames;  // row 0 of the next frame
         if (r == kStepsPerFrame - 1) {  // next step starts a new frame: the P2 histories were flushed by the four zero
             L.r = 0;                    // rows, the sums hold rounding residue

@@ -14,6 +14,7 @@ Same names, argument meaning and error behaviour as the reference's call sites u
 from __future__ import annotations
 
 import ctypes as C
+from collections import deque
 
 from . import _ffi
 
@@ -68,6 +69,11 @@ class VpdqHash:
         return hash(self._b)
 
 
+def _PUSH_NOCOPY(handle, frame: bytes, n: int) -> int:
+    """vpdq_b200_hasher_push_nocopy with a bytes object as the source (ctypes passes the object's own buffer)"""
+    return _ffi.lib().vpdq_b200_hasher_push_nocopy(handle, frame, n)
+
+
 def _ptr(buf):
     """-> (void*, nbytes, keep-alive) for bytes / bytearray / memoryview / numpy; no copy when the
     buffer is contiguous (bytes are passed by pointer)."""
@@ -82,13 +88,21 @@ def _ptr(buf):
 
 
 class VideoHasher:
-    """One video's streaming hasher (vpdqpy.py:113-119).  Frames are staged in a pinned ring, copied to
-    HBM and hashed in batches while further frames are still being pushed; ``hash_frame`` blocks only when
-    the ring is full (the reference's back-pressure, vpdqpy.py:115-117)."""
+    """One video's streaming hasher (vpdqpy.py:113-119).  A handle is pure bookkeeping: every hasher of a device
+    feeds that device's submission service (csrc/hash_service.h), which copies the frames into a shared pinned
+    ring with a pool of copy threads, uploads them and hashes frames of ALL live hashers together;
+    ``hash_frame`` blocks only when the ring is full (the reference's back-pressure, vpdqpy.py:115-117) and
+    ``finish`` waits for this video's frames only.
+
+    ``hash_frame(bytes)`` does not copy on the caller's thread: ``bytes`` is immutable, so the hasher keeps a
+    reference until the copy workers are done with it (at most a ring's worth of frames) and returns at once.
+    Mutable buffers (bytearray, numpy) are copied before the call returns."""
 
     def __init__(self, average_fps: int, width: int, height: int, num_threads: int = 0, *, device: int | None = None,
                  channels: int = 3):
         self._h = None
+        self._held: deque = deque()  # (frame index, bytes object) still being read by the copy workers
+        self._n = 0
         self._frame_bytes = int(width) * int(height) * int(channels)
         self.average_fps = int(average_fps)  # unused, as in the reference (vpdqpy.py:110-112)
         dev = _ffi.default_device() if device is None else int(device)
@@ -104,10 +118,29 @@ class VideoHasher:
 
     def hash_frame(self, frame) -> None:
         """frame: ``width*height*3`` bytes, RGB24 row-major (vpdqpy.py:118)."""
+        if type(frame) is bytes:  # immutable: hand the pointer over, keep the object alive, return at once
+            if len(frame) != self._frame_bytes:
+                raise ValueError(f"frame has {len(frame)} bytes, expected {self._frame_bytes}")
+            rc = _PUSH_NOCOPY(self._handle(), frame, 1)
+            if rc:
+                _ffi.check(rc)
+            self._n += 1
+            self._held.append((self._n, frame))
+            if not (self._n & 15):
+                self._release_consumed()
+            return
         p, n, _keep = _ptr(frame)
         if n != self._frame_bytes:
             raise ValueError(f"frame has {n} bytes, expected {self._frame_bytes}")
         _ffi.check(_ffi.lib().vpdq_b200_hasher_push(self._handle(), p, 1))
+        self._n += 1
+
+    def _release_consumed(self) -> None:
+        done = C.c_int64(0)
+        _ffi.lib().vpdq_b200_hasher_consumed(self._h, C.byref(done))
+        held = self._held
+        while held and held[0][0] <= done.value:
+            held.popleft()
 
     def hash_frames(self, frames) -> None:
         """Batch form of hash_frame: one contiguous buffer holding a whole number of frames."""
@@ -115,6 +148,7 @@ class VideoHasher:
         if n % self._frame_bytes:
             raise ValueError(f"buffer of {n} bytes is not a whole number of {self._frame_bytes}-byte frames")
         _ffi.check(_ffi.lib().vpdq_b200_hasher_push(self._handle(), p, n // self._frame_bytes))
+        self._n += n // self._frame_bytes
 
     def finish(self, *, return_all: bool = False):
         """-> VpdqHash of the frames with quality >= 31, in push order (vpdqpy.py:119, DedupeDB.py:550-553).
@@ -127,7 +161,11 @@ class VideoHasher:
         kept = C.c_int64(0)
         all_h = C.create_string_buffer(cap * _ffi.HASH_BYTES) if return_all else None
         all_q = (C.c_int32 * cap)() if return_all else None
-        _ffi.check(L.vpdq_b200_hasher_finish(self._handle(), _ffi.QUALITY_KEEP, out, cap, C.byref(kept), all_h, all_q))
+        try:
+            _ffi.check(L.vpdq_b200_hasher_finish(self._handle(), _ffi.QUALITY_KEEP, out, cap, C.byref(kept), all_h, all_q))
+        finally:
+            self._held.clear()  # finish() returns only when every frame has been consumed
+            self._n = 0
         phash = VpdqHash(out.raw[: kept.value * _ffi.HASH_BYTES])
         if return_all:
             return phash, all_h.raw[: n.value * _ffi.HASH_BYTES], list(all_q[: n.value])
@@ -136,7 +174,8 @@ class VideoHasher:
     def close(self) -> None:
         h, self._h = self._h, None
         if h is not None and h.value:
-            _ffi.lib().vpdq_b200_hasher_destroy(h)
+            _ffi.lib().vpdq_b200_hasher_destroy(h)  # waits for frames still in flight
+        self._held.clear()
 
     def __del__(self):
         try:

@@ -54,9 +54,13 @@ typedef enum vpdq_b200_status {
 VPDQ_B200_API const char* vpdq_b200_last_error(void);
 VPDQ_B200_API int vpdq_b200_abi_version(void);
 VPDQ_B200_API int vpdq_b200_device_count(int* count);
-/* Self-check after a device synchronise: 0 = healthy; bit 0 = a TMA copy inside the fused PDQ kernel never
- * completed (its bounded wait gave up) -- results of that launch are then invalid. */
+/* Self-check after a device synchronise: 0 = healthy; bit 0 = a TMA copy inside a PDQ kernel never completed (its
+ * bounded wait gave up) -- results of that launch are then invalid.  Every host-pointer entry point (hash_frames_host,
+ * the hasher handle) reads the same flags at its own synchronisation point and fails with VPDQ_B200_ERR_CUDA; callers
+ * of the stream-ordered *_dev entry points check here after they synchronise. */
 VPDQ_B200_API int vpdq_b200_debug_flags(int device, int* flags);
+/* test hook: set (value != 0) or clear the flags above, to exercise the failure path */
+VPDQ_B200_API int vpdq_b200_debug_force_timeout(int device, int value);
 /* Which CUDA pipeline hashes RGB24 frames (all bit-identical; for A/B measurements and cross-checks):
  * 2 = frame-pair fused kernel kx_fused_jarosz2 (default), 1 = one-frame fused kernel kx_fused_jarosz,
  * 0 = v1 line kernels.  Initial value from the environment variable VPDQ_B200_PDQ_IMPL (fused | lines).
@@ -108,11 +112,25 @@ VPDQ_B200_API int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int ch
  *   create  <- vpdq.VideoHasher(average_fps, width, height, num_threads)        vpdqpy.py:113
  *   push    <- hasher.hash_frame(bytes)   (blocks while the staging ring is full) vpdqpy.py:115-118
  *   finish  <- hasher.finish(): hashes of the frames with quality >= 31, in push order  vpdqpy.py:119
- * `num_threads` is accepted for signature compatibility and ignored (the GPU is the pool). */
+ * `num_threads` is accepted for signature compatibility and ignored (the GPU is the pool).
+ *
+ * A handle owns no device or pinned memory: all handles of a (device, channels) pair feed ONE submission service
+ * (created on first use: a pinned + a device ring of VPDQ_B200_ARENA_FRAMES [256] frame slots, VPDQ_B200_COPY_THREADS
+ * [min(8, cores/2)] copy workers, one pump thread).  Frames of different handles share uploads and kernel launches;
+ * finish() waits for the handle's own frames only.  Handles may be used from different threads concurrently (one
+ * thread per handle at a time). */
 typedef struct vpdq_b200_hasher vpdq_b200_hasher;
 VPDQ_B200_API int vpdq_b200_hasher_create(int device, int width, int height, int channels, int num_threads,
                             vpdq_b200_hasher** out);
+/* copies the frames out of h_frames before returning (the caller may reuse the buffer at once) */
 VPDQ_B200_API int vpdq_b200_hasher_push(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames);
+/* Same, but returns as soon as the frames are queued: the copy workers read h_frames LATER.  The caller must keep the
+ * memory alive and unchanged until vpdq_b200_hasher_consumed() has passed these frames or finish() / destroy()
+ * returned.  (The Python binding uses it for immutable `bytes` frames, which it simply keeps a reference to:
+ * hash_frame(bytes(frame.planes[0])), vpdqpy.py:118, then costs one queue insertion on the caller's thread.) */
+VPDQ_B200_API int vpdq_b200_hasher_push_nocopy(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames);
+/* number of leading frames (in push order, since the last finish) whose source memory is no longer needed */
+VPDQ_B200_API int vpdq_b200_hasher_consumed(vpdq_b200_hasher* h, int64_t* n);
 /* total frames pushed so far (upper bound for finish's capacity) */
 VPDQ_B200_API int vpdq_b200_hasher_pushed(vpdq_b200_hasher* h, int64_t* n);
 /* Writes kept hashes (quality >= quality_keep) to h_hashes [cap][32]; *n_kept = number kept.
