@@ -305,34 +305,39 @@ int vpdq_b200_pdq_hash_frames_dev(const uint8_t* d_frames, int channels, int64_t
                                     nullptr, d_scratch, scratch_bytes, stream);
 }
 
-// Per-device workspace of the one-shot host call, kept between calls (grow-only) so that a caller that
-// hashes batch after batch pays for cudaMalloc / stream creation once.
+// Per-device workspace of the one-shot host call for PINNED callers, kept between calls so that a caller that hashes
+// batch after batch pays for cudaMalloc / stream creation once.  kHostStages stages of kHostChunk frames in flight on
+// as many streams: the H2D copy of a chunk overlaps the kernels of the previous ones, and the small chunk keeps the
+// unoverlapped head (first copy) and tail (last kernels) of the pipeline short.
 namespace {
+constexpr int kHostStages = 4;
+constexpr int64_t kHostChunk = 64;  // frames per stage (50 MB of RGB24)
 struct HostPipe {
     bool ready = false;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t freed[2] = {nullptr, nullptr};
-    uint8_t* d_in[2] = {nullptr, nullptr};
-    void* d_scr[2] = {nullptr, nullptr};
-    uint8_t* d_hash[2] = {nullptr, nullptr};
-    int32_t* d_q[2] = {nullptr, nullptr};
+    cudaStream_t st[kHostStages] = {};
+    uint8_t* d_in[kHostStages] = {};
+    void* d_scr[kHostStages] = {};
+    uint8_t* d_hash[kHostStages] = {};
+    int32_t* d_q[kHostStages] = {};
+    int* h_flags = nullptr;  // pinned [kHostStages][4]
     size_t in_bytes = 0, scr_bytes = 0;
     std::mutex mu;
 };
-constexpr int64_t kHostChunk = 256;  // frames per H2D/compute stage (201 MB of RGB24)
 HostPipe g_pipes[64];
 
 int host_pipe_prepare(HostPipe& p, size_t in_bytes, size_t scr_bytes) {
     if (!p.ready) {
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kHostStages; ++b) {
             VPDQ_CUDA(cudaStreamCreateWithFlags(&p.st[b], cudaStreamNonBlocking));
             VPDQ_CUDA(cudaMalloc(&p.d_hash[b], kHostChunk * 32));
             VPDQ_CUDA(cudaMalloc(&p.d_q[b], kHostChunk * sizeof(int32_t)));
         }
+        VPDQ_CUDA(cudaHostAlloc(&p.h_flags, kHostStages * 4 * sizeof(int), cudaHostAllocDefault));
         p.ready = true;
     }
     if (in_bytes > p.in_bytes) {
-        for (int b = 0; b < 2; ++b) {
+        p.in_bytes = 0;  // (a failed cudaMalloc below must not leave a stale size behind)
+        for (int b = 0; b < kHostStages; ++b) {
             if (p.d_in[b]) VPDQ_CUDA(cudaFree(p.d_in[b]));
             p.d_in[b] = nullptr;
             VPDQ_CUDA(cudaMalloc(&p.d_in[b], in_bytes));
@@ -340,7 +345,8 @@ int host_pipe_prepare(HostPipe& p, size_t in_bytes, size_t scr_bytes) {
         p.in_bytes = in_bytes;
     }
     if (scr_bytes > p.scr_bytes) {
-        for (int b = 0; b < 2; ++b) {
+        p.scr_bytes = 0;
+        for (int b = 0; b < kHostStages; ++b) {
             if (p.d_scr[b]) VPDQ_CUDA(cudaFree(p.d_scr[b]));
             p.d_scr[b] = nullptr;
             VPDQ_CUDA(cudaMalloc(&p.d_scr[b], scr_bytes));
@@ -348,6 +354,15 @@ int host_pipe_prepare(HostPipe& p, size_t in_bytes, size_t scr_bytes) {
         p.scr_bytes = scr_bytes;
     }
     return VPDQ_B200_OK;
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
 }
 }  // namespace
 
@@ -368,18 +383,39 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
         set_error("device index %d out of range", dev);
         return VPDQ_B200_ERR_INVALID;
     }
+    const size_t fb = (size_t)kPlane * channels;
+
+    if (!is_pinned_host(h_frames)) {
+        // pageable source: a DMA engine cannot read it, so every byte has to be copied into pinned memory by the
+        // CPU first -- the submission service does that with its copy workers in parallel with the uploads
+        Service* svc = nullptr;
+        rc = get_service(dev, channels, &svc);
+        if (rc) return rc;
+        vpdq_service::HasherState st;
+        rc = svc->push(&st, h_frames, n_frames, false);
+        const int err = svc->wait_all(&st);
+        if (rc || err) {
+            set_error("hash_frames_host: the hashing service of device %d failed (%d)", dev, rc ? rc : err);
+            return VPDQ_B200_ERR_CUDA;
+        }
+        std::lock_guard<std::mutex> lk(st.mu);
+        memcpy(h_hashes, st.hashes.data(), (size_t)n_frames * 32);
+        memcpy(h_quality, st.quality.data(), (size_t)n_frames * sizeof(int32_t));
+        return VPDQ_B200_OK;
+    }
+
     HostPipe& p = g_pipes[dev];
     std::lock_guard<std::mutex> lk(p.mu);
-
-    // two stages in flight on two streams: the H2D copy of chunk c+1 overlaps the kernels of chunk c
     const int64_t chunk = n_frames < kHostChunk ? n_frames : kHostChunk;
-    const size_t fb = (size_t)kPlane * channels;
-    const size_t scr = pdq_scratch_bytes(chunk);
-    rc = host_pipe_prepare(p, (size_t)chunk * fb, scr);
+    const size_t scr = (size_t)kHostChunk * fused_scratch_per_frame() > pdq_scratch_bytes(1)
+                           ? (size_t)kHostChunk * fused_scratch_per_frame()
+                           : pdq_scratch_bytes(1);
+    rc = host_pipe_prepare(p, (size_t)kHostChunk * (size_t)kPlane * 3, pdq_impl() == 0 ? pdq_scratch_bytes(kHostChunk) : scr);
     if (rc) return rc;
+    memset(p.h_flags, 0, kHostStages * 4 * sizeof(int));
     int c = 0;
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, ++c) {
-        const int b = c & 1;
+        const int b = c % kHostStages;
         const int64_t nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         VPDQ_CUDA(cudaMemcpyAsync(p.d_in[b], h_frames + (size_t)f0 * fb, (size_t)nf * fb, cudaMemcpyHostToDevice,
                                   p.st[b]));
@@ -391,10 +427,17 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
         VPDQ_CUDA(cudaMemcpyAsync(h_quality + f0, p.d_q[b], (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                   p.st[b]));
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kHostStages; ++b) {
+        if (rc == VPDQ_B200_OK) rc = pdq_timeout_flags_async(p.h_flags + 4 * b, p.st[b]);
         cudaError_t e = cudaStreamSynchronize(p.st[b]);
         if (e != cudaSuccess && rc == VPDQ_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
+    if (rc == VPDQ_B200_OK)
+        for (int i = 0; i < kHostStages * 4; ++i)
+            if (p.h_flags[i]) {
+                set_error("a TMA copy inside the PDQ kernel never completed: results invalid");
+                rc = VPDQ_B200_ERR_CUDA;
+            }
     return rc;
 }
 

@@ -232,15 +232,17 @@ __global__ void __launch_bounds__(kSysThreads, 1)
 
     const int t_last = last_step(F);
 #pragma unroll 1
-    for (int t = kFirstStep; t <= t_last; t += 8) {  // (steps past t_last only see rows that are not live)
+    for (int t = kFirstStep; t <= t_last; t += kBody) {  // (steps past t_last only see rows that are not live)
         step(t, std::integral_constant<int, 0>{});
         step(t + 1, std::integral_constant<int, 1>{});
         step(t + 2, std::integral_constant<int, 2>{});
         step(t + 3, std::integral_constant<int, 3>{});
-        step(t + 4, std::integral_constant<int, 4>{});
-        step(t + 5, std::integral_constant<int, 5>{});
-        step(t + 6, std::integral_constant<int, 6>{});
-        step(t + 7, std::integral_constant<int, 7>{});
+        if (kBody == 8) {
+            step(t + 4, std::integral_constant<int, 4>{});
+            step(t + 5, std::integral_constant<int, 5>{});
+            step(t + 6, std::integral_constant<int, 6>{});
+            step(t + 7, std::integral_constant<int, 7>{});
+        }
     }
     for (int E = waited + 1; E <= issued; ++E) wait(E);  // no copy may be in flight when the CTA retires
 }

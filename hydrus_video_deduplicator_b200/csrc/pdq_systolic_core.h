@@ -151,6 +151,10 @@ constexpr int kRing = 16;            // stream rows per group ring
 constexpr int kBoxRows = 4;          // stream rows per TMA box
 constexpr int kGroupLanes = 4;
 constexpr int kGroups = 32 / kGroupLanes;  // 8
+#ifndef VPDQS_BODY
+#define VPDQS_BODY 4
+#endif
+constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4 or 8 (see LaneState)
 constexpr int kFirstStep = -8;       // the step loop starts here (a multiple of 8; steps < 0 only prepare lane 0's first row)
 constexpr int kIssueLead = 10;       // ISSUE(E) at step 4 E - 10
 constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
@@ -227,17 +231,20 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
     return c.s;
 }
 
-// The step loop is unrolled by 8: T8 = step & 7 selects the history slot (T8 & 3) and which of two register sets a
-// value is read from / written to, so that a new value is computed straight into its final register while the old
-// one is still being consumed (no register copies): the lumas alternate every step, the histories every 4 steps.
+// The step loop is unrolled by kBody: T8 = step & 7 selects the history slot (T8 & 3) and which of two register sets
+// a value is read from / written to, so that a new value is computed straight into its final register while the old
+// one is still being consumed (no register copies): the lumas alternate every step and, with kBody = 8, the
+// histories every 4 steps.  Measured on B200: the 8-step body saves 16 MOVs per step but its hot path (35 KB)
+// overflows the 32 KB L1.5 instruction cache ("no_instructions" stalls 3 % -> 19 %, 2 % slower overall), so the
+// product builds kBody = 4 (one history set; ptxas inserts the copies).
 struct LaneState {
     F2 s2[kCols / 2];         // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start
                               // of a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
                               // (one set of registers for both: see the tail of lane_step for the divisor-3 rows)
-    F2 h2[2][4][kCols / 2];   // P2 histories (the last four inputs): the value written at step u is h2[set(u)][u & 3]
+    F2 h2[kBody / 4][4][kCols / 2];   // P2 histories (the last four inputs): the value written at step u is h2[set(u)][u & 3]
     F2 x[2][kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..) in x[step & 1], computed during the previous step
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
-    F2 h4[2][4];
+    F2 h4[kBody / 4][4];
     RowChain in1, in3;        // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
     int r, f;                 // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
     // predicates that only change in the rare-row tail (so that the common path evaluates no row comparisons):
@@ -248,12 +255,12 @@ struct LaneState {
         for (int p = 0; p < kCols / 2; ++p) {
             s2[p] = f2_splat(0.0f);
             VPDQS_UNROLL
-            for (int j = 0; j < 4; ++j) h2[0][j][p] = h2[1][j][p] = f2_splat(0.0f);
+            for (int j = 0; j < 4; ++j) h2[0][j][p] = h2[kBody / 4 - 1][j][p] = f2_splat(0.0f);
             x[0][p] = x[1][p] = f2_splat(0.0f);
         }
         s4 = f2_splat(0.0f);
         VPDQS_UNROLL
-        for (int j = 0; j < 4; ++j) h4[0][j] = h4[1][j] = f2_splat(0.0f);
+        for (int j = 0; j < 4; ++j) h4[0][j] = h4[kBody / 4 - 1][j] = f2_splat(0.0f);
         in1 = row_zero();
         in3 = row_zero();
         // stream row of lane l at the first step = kFirstStep - l < 0: rows of the virtual frame -1 (never live)
@@ -264,7 +271,7 @@ struct LaneState {
     }
 };
 // where the history value written at step u (u & 7 = U8) lives
-constexpr int hist_set(int U8) { return ((((U8 + 8) & 7) >> 2) & 1) ^ 1; }
+constexpr int hist_set(int U8) { return kBody == 8 ? ((((U8 + 8) & 7) >> 2) & 1) ^ 1 : 0; }
 constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
 
 // M = 2^23 + byte: the byte at offset b of the little-endian word array spliced into the mantissa of 2^23 (PRMT)
@@ -302,7 +309,7 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
 template <int CH, int T8, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
-    constexpr int J = T8 & 3, PX = T8 & 1, PH = (T8 >> 2) & 1;
+    constexpr int J = T8 & 3, PX = T8 & 1, PH = kBody == 8 ? (T8 >> 2) & 1 : 0, PHW = kBody == 8 ? PH ^ 1 : 0;
     const int r = L.r;
     RowChain c1 = L.in1, c3 = L.in3;
     float z0 = 0.0f, z1 = 0.0f;
@@ -325,7 +332,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         const F2 old = L.h2[PH][J][p], prev = L.s2[p];
         F2 s = f2_add(prev, v);
         s = f2_sub(s, old);
-        L.h2[PH ^ 1][J][p] = v;
+        L.h2[PHW][J][p] = v;
         L.s2[p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
@@ -340,7 +347,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         const F2 old = L.h4[PH][J];
         F2 s = f2_add(L.s4, z);
         s = f2_sub(s, old);
-        L.h4[PH ^ 1][J] = z;
+        L.h4[PHW][J] = z;
         L.s4 = s;
         if (L.zmask && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
             emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
