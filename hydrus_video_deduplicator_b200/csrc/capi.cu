@@ -451,8 +451,8 @@ int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int widt
         return VPDQ_B200_ERR_INVALID;
     }
     return pdq_impl() == 1   ? fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream)
-           : pdq_impl() == 3 ? systolic_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream)
-                             : fused2_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream);
+           : pdq_impl() == 2 ? fused2_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream)
+                             : systolic_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream);
 }
 
 int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width, uint8_t* d_dst,

@@ -486,7 +486,7 @@ int pdq_impl() {
     int v = g_pdq_impl.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("VPDQ_B200_PDQ_IMPL");
-        v = (e && strcmp(e, "lines") == 0) ? 0 : (e && strcmp(e, "fused") == 0) ? 1 : (e && strcmp(e, "systolic") == 0) ? 3 : 2;
+        v = (e && strcmp(e, "lines") == 0) ? 0 : (e && strcmp(e, "fused") == 0) ? 1 : (e && strcmp(e, "fused2") == 0) ? 2 : 3;
         g_pdq_impl.store(v, std::memory_order_relaxed);
     }
     return v;

@@ -238,9 +238,10 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
 // overflows the 32 KB L1.5 instruction cache ("no_instructions" stalls 3 % -> 19 %, 2 % slower overall), so the
 // product builds kBody = 4 (one history set; ptxas inserts the copies).
 struct LaneState {
-    F2 s2[kCols / 2];         // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start
-                              // of a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
-                              // (one set of registers for both: see the tail of lane_step for the divisor-3 rows)
+    F2 s2[2][kCols / 2];      // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair; read from
+                              // s2[step & 1], written to the other set.  At the start of a step they are ALSO the P2
+                              // outputs of the previous step, which P3 consumes in this one (one value for both: see the
+                              // tail of lane_step for the divisor-3 rows)
     F2 h2[kBody / 4][4][kCols / 2];   // P2 histories (the last four inputs): the value written at step u is h2[set(u)][u & 3]
     F2 x[2][kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..) in x[step & 1], computed during the previous step
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
@@ -253,7 +254,7 @@ struct LaneState {
     VPDQS_HD void init(int lane) {
         VPDQS_UNROLL
         for (int p = 0; p < kCols / 2; ++p) {
-            s2[p] = f2_splat(0.0f);
+            s2[0][p] = s2[1][p] = f2_splat(0.0f);
             VPDQS_UNROLL
             for (int j = 0; j < 4; ++j) h2[0][j][p] = h2[kBody / 4 - 1][j][p] = f2_splat(0.0f);
             x[0][p] = x[1][p] = f2_splat(0.0f);
@@ -329,11 +330,11 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         const float v1 = row_feed(c1, x.y);
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
-        const F2 old = L.h2[PH][J][p], prev = L.s2[p];
+        const F2 old = L.h2[PH][J][p], prev = L.s2[PX][p];
         F2 s = f2_add(prev, v);
         s = f2_sub(s, old);
         L.h2[PHW][J][p] = v;
-        L.s2[p] = s;
+        L.s2[PX ^ 1][p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
         const float u0 = row_feed(c3, prev.x);
@@ -369,7 +370,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         // running sum (its subtractions are all of zeros there).
         if (r == 2 || r == kImageRows) {
             VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = edge3(L.s2[p]);
+            for (int p = 0; p < kCols / 2; ++p) L.s2[PX ^ 1][p] = edge3(L.s2[PX ^ 1][p]);
         }
         if (r == 2) {  // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
             L.s4 = f2_splat(0.0f);
@@ -378,7 +379,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         if (r == 3) {
             VPDQS_UNROLL
             for (int p = 0; p < kCols / 2; ++p)
-                L.s2[p] = f2_add(f2_add(f2_add(L.h2[hist_set(T8 - 3)][hist_slot(T8 - 3)][p],
+                L.s2[PX ^ 1][p] = f2_add(f2_add(f2_add(L.h2[hist_set(T8 - 3)][hist_slot(T8 - 3)][p],
                                                L.h2[hist_set(T8 - 2)][hist_slot(T8 - 2)][p]),
                                         L.h2[hist_set(T8 - 1)][hist_slot(T8 - 1)][p]),
                                  L.h2[hist_set(T8)][hist_slot(T8)][p]);
@@ -390,7 +391,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
             L.r = 0;                    // rows, the sums hold rounding residue
             ++L.f;
             VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = f2_splat(0.0f);
+            for (int p = 0; p < kCols / 2; ++p) L.s2[PX ^ 1][p] = f2_splat(0.0f);
         }
     }
 }

@@ -79,7 +79,7 @@ def test_jarosz_planes_entry_point(torch_dev):
 
 
 def test_two_hashers_interleaved():
-    """Two VideoHashers fed alternately (each owns its stream, ring and scratch): no cross-talk."""
+    """Two VideoHashers fed alternately (their frames interleave in the shared ring and launches): no cross-talk."""
     fa, fb = synth.synth_frames(70, seed=50), synth.synth_frames(45, seed=51)
     ha, hb = vpdq.VideoHasher(1, 512, 512, 0), vpdq.VideoHasher(1, 512, 512, 4)
     for k in range(70):
@@ -138,6 +138,128 @@ def test_video_hasher_streaming_matches_oracle():
     hasher.close()
 
 
+@pytest.mark.parametrize("n", [32, 96, 128, 256, 257])
+def test_video_hasher_exact_multiples_of_the_staging_sizes(n):
+    """Frame counts that are exact multiples of the staging ring / launch sizes (round 1's per-hasher ring returned
+    96 frames as B,C,A -- ADVICE r01): hashes must come back in push order."""
+    frames = synth.synth_frames(min(n, 48), seed=100 + n)
+    frames = np.concatenate([frames] * ((n + len(frames) - 1) // len(frames)))[:n]
+    frames = np.ascontiguousarray(frames)
+    frames[:, 0, 0, 0] = np.arange(n) % 251  # make every frame distinct (does not change the quality filter much)
+    hasher = vpdq.VideoHasher(1, 512, 512, 0)
+    for k in range(n):
+        hasher.hash_frame(frames[k].tobytes())
+    phash, all_h, all_q = hasher.finish(return_all=True)
+    hasher.close()
+    ref_h, ref_q = oracle.pdq_hash_frames(frames, nthreads=8)
+    assert all_h == ref_h.tobytes() and all_q == ref_q.tolist()
+    assert phash.bytes == ref_h[ref_q >= 31].tobytes()
+
+
+def test_concurrent_hashers_from_threads_share_the_service():
+    """Several Python threads, one VideoHasher per video (vpdqpy.py:113-119), 10-frame and 37-frame videos: frames
+    of different videos are coalesced into common launches by the per-device service; every video must get exactly
+    its own hashes, in order."""
+    import threading
+
+    n_threads, per_thread = 4, 6
+    base = synth.synth_frames(48, seed=77)
+    want, got = {}, {}
+
+    def video_frames(t, v):
+        n = 10 if v % 2 == 0 else 37
+        f = np.ascontiguousarray(np.roll(base, 7 * t + v, axis=0)[:n])
+        f[:, 1, 1, 1] = (t * 16 + v) % 256
+        return f
+
+    def work(t):
+        for v in range(per_thread):
+            f = video_frames(t, v)
+            h = vpdq.VideoHasher(1, 512, 512, 0)
+            for k in range(len(f)):
+                h.hash_frame(f[k].tobytes())
+            got[(t, v)] = h.finish().bytes
+            h.close()
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for t in range(n_threads):
+        for v in range(per_thread):
+            want[(t, v)] = oracle.video_hash(video_frames(t, v), nthreads=8)
+    assert got == want
+
+
+def test_hash_frame_snapshot_semantics():
+    """hash_frame(bytes) keeps a reference instead of copying; a MUTABLE buffer must be copied before the call
+    returns (the caller may overwrite it at once, as a decode loop reusing one frame buffer does)."""
+    frames = synth.synth_frames(6, seed=5)
+    buf = bytearray(frames[0].tobytes())
+    hasher = vpdq.VideoHasher(1, 512, 512, 0)
+    for k in range(6):
+        buf[:] = frames[k].tobytes()
+        hasher.hash_frame(buf)       # mutable: copied inside the call
+        buf[:] = b"\x00" * len(buf)  # clobber immediately
+    for k in range(6):
+        hasher.hash_frame(frames[k].tobytes())  # bytes: zero-copy hand-over, the temporary is dropped by the caller
+    _, all_h, _ = hasher.finish(return_all=True)
+    hasher.close()
+    ref_h, _ = oracle.pdq_hash_frames(frames, nthreads=6)
+    assert all_h == ref_h.tobytes() * 2
+
+
+def test_tma_timeout_flag_fails_loudly(torch_dev):
+    """VERDICT r01 weak 6 / ADVICE: a bounded TMA wait that gives up must turn into an error at the host entry points,
+    not into an OK with garbage hashes.  The flag is forced through the test hook; the pinned one-shot call must fail
+    while it is set and work again once it is cleared.  (The hasher service makes the error sticky for the process, so
+    that path is exercised in a child process.)"""
+    import ctypes as C
+    import subprocess
+    import sys
+
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    torch, dev = torch_dev
+    frames = synth.synth_frames(4, seed=3)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    hashes = torch.empty((4, 32), dtype=torch.uint8).pin_memory()
+    quality = torch.empty((4,), dtype=torch.int32).pin_memory()
+
+    def call():
+        return _ffi.lib().vpdq_b200_pdq_hash_frames_host(C.c_void_p(h_frames.data_ptr()), 3, 4, 512, 512,
+                                                         C.c_void_p(hashes.data_ptr()), C.c_void_p(quality.data_ptr()), 0)
+
+    assert call() == _ffi.OK
+    try:
+        _ffi.check(_ffi.lib().vpdq_b200_debug_force_timeout(0, 1))
+        assert _ffi.debug_flags(0) != 0
+        assert call() == _ffi.ERR_CUDA
+        assert b"TMA" in _ffi.lib().vpdq_b200_last_error()
+    finally:
+        _ffi.check(_ffi.lib().vpdq_b200_debug_force_timeout(0, 0))
+    assert call() == _ffi.OK and _ffi.debug_flags(0) == 0
+    ref_h, _ = oracle.pdq_hash_frames(frames, nthreads=4)
+    assert hashes.numpy().tobytes() == ref_h.tobytes()
+
+    child = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from hydrus_video_deduplicator_b200 import _ffi, vpdq\n"
+        "h = vpdq.VideoHasher(1, 512, 512, 0)\n"
+        "h.hash_frame(bytes(786432)); h.finish()\n"
+        "_ffi.check(_ffi.lib().vpdq_b200_debug_force_timeout(0, 1))\n"
+        "h.hash_frame(bytes(786432))\n"
+        "try:\n"
+        "    h.finish(); print('NO ERROR')\n"
+        "except _ffi.VpdqB200Error as e:\n"
+        "    print('LOUD', e.code)\n"
+    ) % str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
+    assert "LOUD -2" in out.stdout, out.stdout + out.stderr
+
+
 def test_host_batch_call_matches_oracle():
     import ctypes as C
 
@@ -176,32 +298,40 @@ def test_large_batch_properties(torch_dev):
 
 
 def test_config1_100k_frames(torch_dev):
-    """BASELINE configs[1]: 100k synthetic frames through the device-resident path, in 8192-frame pieces.
-    Full-size checks: split invariance (two different batchings give identical bytes), popcount 128 on every
-    non-degenerate frame, and an oracle comparison on a strided sample."""
+    """BASELINE configs[1] / SURVEY 8d config 2: 100 000 synthetic frames through the device-resident path, and ALL of
+    them -- 25.6 M hash bits + 100 k quality values -- compared with the oracle (run on every host core).  The mix is
+    biased toward the order-sensitive classes: one third smooth gradients, plus near-flat low-amplitude frames whose
+    DCT coefficients sit within rounding noise of each other.  Also split invariance (two batchings, identical bytes)."""
+    import os
+
     torch, dev = torch_dev
     from bench import device_frames
     from hydrus_video_deduplicator_b200 import device
 
-    total, piece = 100_000, 8192
-    checked = 0
+    total, piece = 100_000, 4096
+    cores = os.cpu_count() or 8
+    stage = torch.empty((piece, 512, 512, 3), dtype=torch.uint8).pin_memory()
+    bad_total, checked = 0, 0
     for p0 in range(0, total, piece):
         n = min(piece, total - p0)
         frames = device_frames(torch, n, dev, seed=p0)
+        frames[3::10] = (frames[3::10] >> 6) + 100          # near-flat: values 100..103
+        frames[7::20] = (frames[7::20] >> 7) * 255          # hard black / white noise
         h1, q1 = device.hash_frames(frames)
         cut = 1 + (p0 // piece) * 37 % (n - 1)
         ha, qa = device.hash_frames(frames[:cut])
         hb, qb = device.hash_frames(frames[cut:])
         assert torch.equal(h1, torch.cat([ha, hb])) and torch.equal(q1, torch.cat([qa, qb]))
-        pop = torch.from_numpy(np.unpackbits(h1.cpu().numpy(), axis=1).sum(axis=1))
-        assert int((pop != 128).sum()) == 0
-        idx = torch.arange(p0 % 7, n, 1021, device=dev)
-        ref_h, ref_q = oracle.pdq_hash_frames(frames[idx].cpu().numpy(), nthreads=16)
-        assert h1[idx].cpu().numpy().tobytes() == ref_h.tobytes()
-        assert (q1[idx].cpu().numpy() == ref_q).all()
-        checked += len(idx)
+        stage[:n].copy_(frames, non_blocking=True)
+        torch.cuda.synchronize()
+        ref_h, ref_q = oracle.pdq_hash_frames(stage[:n].numpy(), nthreads=cores)
+        got_h, got_q = h1.cpu().numpy(), q1.cpu().numpy()
+        bad = np.flatnonzero((got_h != ref_h).any(axis=1) | (got_q != ref_q))
+        bad_total += bad.size
+        assert bad.size == 0, f"{bad.size} of {n} frames differ from the oracle in piece {p0}, first {p0 + bad[:5]}"
+        checked += n
         del frames
-    assert checked >= 100
+    assert checked == total and bad_total == 0
 
 
 def test_fused_kernel_is_deterministic_under_load(torch_dev):
