@@ -8,12 +8,15 @@ workload "hash" (default; BASELINE.json configs[1]: "hash 100k synthetic frames"
     a step = one pass of the PDQ frame-hash path over one batch of synthetic 512x512 RGB24 frames.
     value = frames/s with the batch already resident in HBM (CUDA events on the launching stream, max over
             ranks); e2e = the same through the host-pointer C ABI call (pinned host memory -> H2D -> kernels
-            -> D2H inside the timed region).  Each step's input (6.4 GB) is far larger than L2 (126 MB).
-    At N = 1 the JSON line also carries the Hamming figures (streaming scan GB/s vs the HBM peak at
-    n_query = 1/2/4/8, and 1M x 1M all-pairs comparisons/s) under "hamming".
-workload "hamming" (BASELINE.json configs[3]): pair-comparisons/s of the all-pairs kernel with the target
-    DB sharded over the ranks (1.25 M hashes per GPU, i.e. 10 M at 8 GPUs), queries replicated, and an
-    NCCL all_gather of the candidate bitmaps every step.
+            -> D2H inside the timed region), next to the measured copy-only roof of the same buffers and to the rates
+            of the reference-shaped API (vpdq.VideoHasher.hash_frame(bytes), one hasher per video, 300- and 10-frame
+            videos).  Each step's input (6.4 GB) is far larger than L2 (126 MB).
+    Every N also carries, under "hamming", BASELINE configs[3]: a FIXED 10 M-hash database (300-frame videos,
+    SURVEY config 3's generator) sharded at video boundaries over the N ranks, a replicated query block, one NCCL
+    all_gather of the candidate bitmaps per step inside the timed region -> pair-comparisons/s, plus the collective's
+    own time.  At N = 1 additionally: streaming scan GB/s vs the HBM peak by resident query count, 1M x 1M all pairs,
+    and the same kernels on a video-like database (dense near-duplicates).
+workload "hamming": the sharded all-pairs line above as the headline value (same config).
 
 --impl reference times the reference's CPU path (the golden-pinned oracle port; the real arithmetic lives
 in the absent hvdaccelerators wheel) on the host cores with all threads, same metric/config.
@@ -47,20 +50,16 @@ def emit(line: dict) -> None:
 
 
 def jarosz_kernel_name() -> str:
-    """The Jarosz kernel the library runs for RGB24 frames (csrc/pdq_kernels.cu pdq_impl())."""
-    return {"fused": "kx_fused_jarosz", "lines": "k1_luma_rowpass+k2_colpass+k3_rowpass_dec"}.get(
-        os.environ.get("VPDQ_B200_PDQ_IMPL", ""), "kx_fused_jarosz2")
+    return "kx_systolic_jarosz"
 
 
 def finalize_kernel_name() -> str:
-    if os.environ.get("VPDQ_B200_PDQ_IMPL", "") == "lines":
-        return "k4_colpass_finalize<false>"
-    return "k4_colpass_finalize<true>" if os.environ.get("VPDQ_B200_FINALIZE", "") == "k4" else "k5_finalize"
+    return "k5_finalize"
 
 
 def measured_traffic_per_frame() -> float | None:
-    """DRAM bytes per frame of the dominant PDQ kernel from the committed ncu capture (profiles/r01_traffic.json)."""
-    p = ROOT / "profiles" / "r01_traffic.json"
+    """DRAM bytes per frame of the dominant PDQ kernel from the committed ncu capture (profiles/r02_traffic.json)."""
+    p = ROOT / "profiles" / "r02_traffic.json"
     try:
         d = json.loads(p.read_text())
         k = d[jarosz_kernel_name()]
@@ -158,18 +157,67 @@ def device_frames(torch, n: int, device, seed: int):
     return out
 
 
+def _pack_bits(torch, bits):
+    """[n, 256] {0,1} uint8 -> [n, 32] uint8, bit k of a hash in byte k >> 3, bit k & 7 (native PDQ order)"""
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.int32, device=bits.device)
+    return (bits.view(-1, 32, 8).to(torch.int32) * w).sum(dim=2).to(torch.uint8)
+
+
+def _flip_bits(torch, h, n_flip, g):
+    """flip n_flip[i] distinct random bits of hash i ([n, 32] uint8; n_flip [n] int64, <= 64)"""
+    n = h.shape[0]
+    order = torch.rand((n, 256), device=h.device, generator=g).argsort(dim=1)[:, :64]       # 64 distinct positions
+    take = torch.arange(64, device=h.device).unsqueeze(0) < n_flip.unsqueeze(1)
+    mask = torch.zeros((n, 256), dtype=torch.uint8, device=h.device)
+    mask.scatter_(1, order, take.to(torch.uint8))
+    return h ^ _pack_bits(torch, mask)
+
+
 def device_hashes(torch, n: int, device, seed: int, planted_frac: float = 0.01):
-    """[n, 32] u8 random hashes with a planted_frac share of near-duplicates (20 flipped bits)."""
+    """SURVEY.md 8d config 3 on the device: [n, 32] u8 random words of popcount exactly 128 (like genuine PDQ hashes,
+    F5) with a planted_frac share of near-duplicates at Hamming distances 0, 2, .., 40 -- both sides of the tolerance
+    31 (the generator of tests/synth.py, restated with torch ops so that 10 M hashes take seconds)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    h = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=device, generator=g)
+    out = torch.empty((n, 32), dtype=torch.uint8, device=device)
+    step = 1 << 19
+    for i0 in range(0, n, step):
+        m = min(step, n - i0)
+        rank = torch.rand((m, 256), device=device, generator=g).argsort(dim=1).argsort(dim=1)
+        out[i0:i0 + m] = _pack_bits(torch, (rank < 128).to(torch.uint8))
     k = int(n * planted_frac)
     if k and n > 2 * k:
         src = torch.randint(0, n // 2, (k,), device=device, generator=g)
         dst = n // 2 + torch.randperm(n - n // 2, device=device, generator=g)[:k]
-        flip = torch.zeros((k, 32), dtype=torch.uint8, device=device)
-        flip[:, :5] = 0x0F
-        h[dst] = h[src] ^ flip
-    return h
+        dist = 2 * torch.randint(0, 21, (k,), device=device, generator=g)
+        for i0 in range(0, k, step):
+            sl = slice(i0, min(k, i0 + step))
+            out[dst[sl]] = _flip_bits(torch, out[src[sl]], dist[sl], g)
+    return out
+
+
+def device_video_hashes(torch, n_videos: int, frames_per_video: int, device, seed: int, dup_frac: float = 0.05):
+    """A video-like database: every video is a random walk (consecutive frames differ in 0..16 bits, so a frame has
+    many neighbours of its own video within the tolerance) and dup_frac of the videos are noisy copies (0..8 bits per
+    frame) of another one -- the match density of a real library, unlike uniformly random hashes.
+    -> ([n_videos * frames_per_video, 32] u8, offsets [n_videos + 1] i64)"""
+    g = torch.Generator(device=device).manual_seed(seed)
+    n = n_videos * frames_per_video
+    out = torch.empty((n_videos, frames_per_video, 32), dtype=torch.uint8, device=device)
+    cur = device_hashes(torch, n_videos, device, seed + 1, planted_frac=0.0)
+    for k in range(frames_per_video):
+        out[:, k] = cur
+        cur = _flip_bits(torch, cur, torch.randint(0, 17, (n_videos,), device=device, generator=g), g)
+    n_dup = int(n_videos * dup_frac)
+    if n_dup:
+        src = torch.randint(0, n_videos // 2, (n_dup,), device=device, generator=g)
+        dst = n_videos // 2 + torch.randperm(n_videos - n_videos // 2, device=device, generator=g)[:n_dup]
+        for i0 in range(0, n_dup, 256):
+            sl = slice(i0, min(n_dup, i0 + 256))
+            flat = out[src[sl]].reshape(-1, 32)
+            flat = _flip_bits(torch, flat, torch.randint(0, 9, (flat.shape[0],), device=device, generator=g), g)
+            out[dst[sl]] = flat.view(-1, frames_per_video, 32)
+    offsets = torch.arange(0, n + 1, frames_per_video, dtype=torch.int64, device=device)
+    return out.view(n, 32), offsets
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -229,7 +277,10 @@ def run_reference(args) -> None:
         value, unit, metric = rate, "frames/s", "frame_hashes_per_sec"
         ms = secs / max(1, args.steps) * 1e3
         sample = f"{args.steps} steps x {per_step} synthetic 512x512 RGB24 frames, {cores} threads (oracle port)"
-        config = hash_config(args, per_step)
+        # same config object as the B200 arm (the metric is a rate; the CPU arm times a bounded SAMPLE of that
+        # workload, described in cpu_baseline.sample)
+        config = hash_config(args, args.batch)
+        config["parallelism"] = f"{args.gpus} x independent shards (no data-path collective)"
     else:
         n = 16384
         for _ in range(max(1, args.warmup) - 1):
@@ -239,7 +290,8 @@ def run_reference(args) -> None:
         ms = sum(s for _, s in rates) / len(rates) * 1e3
         unit, metric = "pair-comparisons/s", "pair_comparisons_per_sec"
         sample = f"{len(rates)} x ({n} x {n}) 256-bit hashes, tolerance 31, {cores} threads (oracle port)"
-        config = hamming_config(args, 1)
+        config = hamming_config(args, args.gpus)
+        config["parallelism"] = f"target DB sharded over {args.gpus} ranks, queries replicated, all_gather of bitmaps"
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -259,9 +311,10 @@ def hash_config(args, frames_per_step: int) -> dict:
 
 
 def hamming_config(args, world: int) -> dict:
-    return {"workload": "all-pairs Hamming search, 256-bit hashes, tolerance 31 (BASELINE configs[2]/[3])",
-            "targets_per_gpu": args.shard_hashes, "queries_per_step": args.query_block,
-            "l2_policy": "L2 flushed between timed iterations by a 256 MB write (DB shard is L2-sized)"}
+    return {"workload": "all-pairs Hamming search, 256-bit hashes, tolerance 31 (BASELINE configs[3]): fixed 10 M-hash DB "
+                        "sharded over the GPUs",
+            "db_hashes": args.shard_db_hashes, "queries_per_step": args.query_block,
+            "l2_policy": "L2 flushed between timed iterations by a 256 MB write"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -346,10 +399,10 @@ def run_b200(args) -> None:
                                  "frac": pipeline_gbs / peak},
                     "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_FRAME,
                     "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
-                    "traffic_source": "profiles/r01_traffic.json (ncu --set full dram__bytes_read+write, per frame x "
+                    "traffic_source": "profiles/r02_traffic.json (ncu --set full dram__bytes_read+write, per frame x "
                                       "frames per launch)",
-                    "note": "bound by the shared-memory pipe (tile hand-over between row and column passes), not by "
-                            "HBM: see DESIGN.md 4.2"}
+                    "note": "one warp per frame, row-pass chain state handed lane to lane: no shared-memory transposes; "
+                            "bound by instruction issue (serial fp32 running sums), see DESIGN.md 4.2"}
 
         # ---- end to end through the host-pointer C ABI (pinned host memory) ----
         import ctypes as C
@@ -379,7 +432,12 @@ def run_b200(args) -> None:
         e2e = {"value": world * e2e_batch * e2e_steps / e2e_s, "unit": "frames/s",
                "h2d_bytes_per_step": e2e_batch * FRAME_BYTES, "d2h_bytes_per_step": e2e_batch * 36,
                "steps": e2e_steps, "frames_per_step": e2e_batch,
-               "api": "vpdq_b200_pdq_hash_frames_host (C ABI, pinned host buffers, 2 streams)"}
+               "api": "vpdq_b200_pdq_hash_frames_host (C ABI, pinned host buffers, 4 stages of 64 frames in flight)"}
+        # the roof of that number: the same pinned buffer copied host -> device and nothing else, all ranks at once
+        roof = copy_roof(torch, h_frames, dev, sync_all, max_over_ranks)
+        e2e["copy_roof"] = {"GB/s_all_ranks": world * roof, "frames/s_all_ranks": world * roof * 1e9 / FRAME_BYTES,
+                            "e2e_over_roof": e2e["value"] / (world * roof * 1e9 / FRAME_BYTES),
+                            "what": "cudaMemcpyAsync of the e2e step's pinned input alone, all ranks concurrently"}
         # the e2e results must equal the device-resident ones
         chk_h, _ = dev_api.hash_frames(pool[0][:e2e_batch])
         assert torch.equal(chk_h.cpu(), h_hash), "e2e hashes differ from the device-resident path"
@@ -388,65 +446,37 @@ def run_b200(args) -> None:
         config["parallelism"] = f"{world} x independent shards (no data-path collective)"
         dtype = "f32"
 
+        del pool[1:]
+        # the reference-shaped API: vpdq.VideoHasher.hash_frame(bytes) per frame, one hasher per video
+        if not args.no_hasher_api:
+            api = hasher_api_section(torch, dev_api, pool[0], local, sync_all, max_over_ranks, world, args)
+            e2e["video_hasher_api"] = api
+        if not args.no_hamming:  # every rank: the sharded search is a collective
+            extra["hamming"] = {"sharded_all_pairs": sharded_pairs_section(torch, hdist, dev, rank, world, flush_l2,
+                                                                          max_over_ranks, sync_all, args)}
         if rank == 0 and world == 1 and not args.no_hamming:
-            extra["hamming"] = hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args)
-        if rank == 0 and world == 1 and not args.no_luma:
-            extra["luma_frames"] = luma_section(torch, dev_api, dev, local, args)
+            extra["hamming"].update(hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args))
+        if not args.no_luma:
+            luma = luma_section(torch, dev_api, dev, local, args, sync_all, max_over_ranks, world)
+            if rank == 0:
+                extra["luma_frames"] = luma
     else:
-        # ---- all-pairs Hamming, DB sharded over ranks, all_gather of candidate bitmaps ----
-        nt, nq = args.shard_hashes, args.query_block
-        shard = device_hashes(torch, nt, dev, seed=77 + rank)
-        queries = device_hashes(torch, nq, dev, seed=5)  # replicated (same seed on every rank)
-        count = torch.zeros((1,), dtype=torch.int64, device=dev)
-        pairs = torch.empty((1 << 20,), dtype=torch.int64, device=dev)
-        bitmap = torch.zeros(((nq + 31) // 32,), dtype=torch.int32, device=dev)
-
-        def step():
-            count.zero_()
-            bitmap.zero_()
-            _ffi.check(_ffi.lib().vpdq_b200_hamming_pairs_dev(
-                queries.data_ptr(), nq, shard.data_ptr(), nt, 31, 0, bitmap.data_ptr(), pairs.data_ptr(), 1 << 20,
-                count.data_ptr(), torch.cuda.current_stream().cuda_stream))
-            return hdist.all_gather_bitmaps(bitmap)
-
-        for _ in range(args.warmup):
-            step()
-        sync_all()
+        # ---- BASELINE configs[3] as the headline: fixed 10 M-hash DB sharded over the ranks ----
         sampler = ClockSampler(local)
         launches0 = _ffi.kernel_launches()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for k in range(args.steps):
-            flush_l2()
-            ev[k][0].record()
-            gathered = step()
-            ev[k][1].record()
-        torch.cuda.synchronize()
-        ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
-        hdist.barrier()
+        sp = sharded_pairs_section(torch, hdist, dev, rank, world, flush_l2, max_over_ranks, sync_all, args)
         clocks = sampler.stop()
         launches = _ffi.kernel_launches() - launches0
-        ms_per_step = ms_total / args.steps
-        value = float(world) * nt * nq / (ms_per_step / 1e3)
-        algo = (nt + nq) * HASH_BYTES
+        ms_per_step = sp["ms_per_step"]
+        value = sp["pair_comparisons_per_s"]
+        algo = (sp["n_db"] // world + sp["n_query"]) * HASH_BYTES
         achieved = algo / (ms_per_step / 1e3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "kernel": "k_hamming_pairs",
                     "note": "all-pairs is POPC-issue bound, not HBM bound (compulsory bytes are tiny); see "
                             "DESIGN.md -- the HBM-bound regime is the streaming scan reported by --workload hash"}
-        # e2e: host query block -> H2D -> kernel -> D2H of the bitmap
-        hq = queries.cpu().pin_memory()
-        hb = torch.empty_like(bitmap, device="cpu").pin_memory()
-        sync_all()
-        t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 5))
-        for _ in range(e2e_steps):
-            queries.copy_(hq, non_blocking=True)
-            g = step()
-            hb.copy_(hdist.or_reduce(g), non_blocking=True)
-            torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": float(world) * nt * nq * e2e_steps / e2e_s, "unit": "pair-comparisons/s",
-               "h2d_bytes_per_step": nq * HASH_BYTES, "d2h_bytes_per_step": int(hb.numel() * 4), "steps": e2e_steps}
+        e2e = sp["e2e"]
+        extra["hamming"] = {"sharded_all_pairs": sp}
         metric, unit = "pair_comparisons_per_sec", "pair-comparisons/s"
         config = hamming_config(args, world)
         config["parallelism"] = f"target DB sharded over {world} ranks, queries replicated, all_gather of bitmaps"
@@ -492,25 +522,185 @@ def cpu_baseline(args, pool0, torch) -> dict:
             "sample": f"16384 x 16384 hashes on {cores} threads ({secs:.1f} s)"}
 
 
-def luma_section(torch, dev_api, dev, local, args) -> dict:
+def copy_roof(torch, h_pinned, dev, sync_all, max_over_ranks) -> float:
+    """GB/s of this rank when every rank copies its pinned e2e input to the device and does nothing else."""
+    d = torch.empty(h_pinned.shape, dtype=h_pinned.dtype, device=dev)
+    for _ in range(2):
+        d.copy_(h_pinned, non_blocking=True)
+    sync_all()
+    reps = 6
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d.copy_(h_pinned, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    return reps * h_pinned.numel() / dt / 1e9
+
+
+def hasher_api_section(torch, dev_api, pool0, local, sync_all, max_over_ranks, world, args) -> dict:
+    """Frames/s through the drop-in surface the reference binds to: vpdq.VideoHasher(1, 512, 512, n).hash_frame(bytes)
+    per sampled frame, one hasher per video, finish() per video (vpdqpy/vpdqpy.py:113-119, dedup.py:346-352).  The
+    frames are Python bytes objects in pageable memory, exactly what bytes(frame.planes[0]) hands over; copies into
+    the pinned ring, uploads, kernels and result read-back are all inside the timed region.  Results are compared
+    with the device-resident path."""
+    import threading
+
+    from hydrus_video_deduplicator_b200 import vpdq
+
+    n_distinct = 96
+    src = pool0[:n_distinct].cpu()
+    want_h, want_q = dev_api.hash_frames(pool0[:n_distinct])
+    want_h, want_q = want_h.cpu().numpy(), want_q.cpu().numpy()
+    frames = [src[k].numpy().tobytes() for k in range(n_distinct)]
+
+    def run_videos(n_videos: int, n_frames: int, first: int, check: bool):
+        ok = True
+        for v in range(n_videos):
+            h = vpdq.VideoHasher(1, 512, 512, 0, device=local)
+            base = (first + v * n_frames) % n_distinct
+            for k in range(n_frames):
+                h.hash_frame(frames[(base + k) % n_distinct])
+            if check and v == 0:
+                ph, all_h, all_q = h.finish(return_all=True)
+                idx = [(base + k) % n_distinct for k in range(n_frames)]
+                ok = ok and all_h == want_h[idx].tobytes() and all_q == want_q[idx].tolist()
+            else:
+                h.finish()
+            h.close()
+        return ok
+
+    out = {"api": "vpdq.VideoHasher.hash_frame(bytes) x n, finish(); one hasher per video; frames are pageable Python "
+                  "bytes", "n_gpus": world}
+    run_videos(2, 40, 0, False)  # warm the service (arena allocation, threads)
+    for name, n_frames, n_videos, threads in (("300_frame_videos", 300, 10, 1), ("10_frame_videos", 10, 300, 1),
+                                              ("10_frame_videos_4_threads", 10, 300, 4)):
+        results = [True] * threads
+        sync_all()
+        t0 = time.perf_counter()
+        if threads == 1:
+            results[0] = run_videos(n_videos, n_frames, 0, True)
+        else:
+            def work(t):
+                results[t] = run_videos(n_videos // threads, n_frames, 7 * t, True)
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        total = (n_videos // threads) * threads * n_frames
+        out[name] = {"frames/s": world * total / dt, "videos": (n_videos // threads) * threads, "frames_per_video": n_frames,
+                     "caller_threads": threads, "bit_identical_to_device_path": bool(all(results))}
+    return out
+
+
+def sharded_pairs_section(torch, hdist, dev, rank, world, flush_l2, max_over_ranks, sync_all, args) -> dict:
+    """BASELINE configs[3]: ONE fixed 10 M-hash database (33 334 videos of 300 frames, SURVEY config 3's generator,
+    same seed on every rank) sharded at video boundaries over the ranks; a replicated block of query hashes (the first
+    rows of the DB, so every query has at least itself as a match); per step one all-pairs launch over this rank's
+    shard and ONE all_gather of the per-query candidate bitmaps (NCCL when N > 1) inside the timed region.
+    The N = 1 line is the same job on one GPU.  This is what the reference does file by file over the whole DB
+    (db/vptree.py:865-902)."""
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    n_db, fpv, nq = args.shard_db_hashes, 300, args.query_block
+    db = device_hashes(torch, n_db, dev, seed=4242)
+    import numpy as np
+
+    offsets = np.arange(0, n_db + fpv, fpv, dtype=np.int64)
+    offsets[-1] = n_db
+    offsets = np.unique(offsets)
+    bounds = hdist.shard_videos(offsets, world)
+    f0, f1 = int(offsets[bounds[rank]]), int(offsets[bounds[rank + 1]])
+    shard = db[f0:f1].clone()
+    queries = db[:nq].clone()
+    del db
+    nt = f1 - f0
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    bitmap = torch.zeros(((nq + 31) // 32,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def search():
+        count.zero_()
+        bitmap.zero_()
+        _ffi.check(_ffi.lib().vpdq_b200_hamming_pairs_dev(queries.data_ptr(), nq, shard.data_ptr(), nt, 31, 0,
+                                                          bitmap.data_ptr(), None, 0, count.data_ptr(), stream))
+
+    def step():
+        search()
+        return hdist.all_gather_bitmaps(bitmap)
+
+    steps = max(1, min(args.steps, args.shard_steps))
+    for _ in range(2):
+        step()
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush_l2()
+        ev[k][0].record()
+        gathered = step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms_per_step = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+    # the collective on its own
+    cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    sync_all()
+    for a, b in cev:
+        a.record()
+        gathered = hdist.all_gather_bitmaps(bitmap)
+        b.record()
+    torch.cuda.synchronize()
+    gather_us = max_over_ranks(statistics.median(a.elapsed_time(b) for a, b in cev) * 1e3)
+    # matches: every rank counted its shard's; sum over ranks, and every query must be flagged (it matches itself)
+    total = count.to(torch.float64).clone()
+    if world > 1:
+        torch.distributed.all_reduce(total)
+    merged = hdist.or_reduce(gathered)
+    flagged = int(sum(bin(int(v) & 0xFFFFFFFF).count("1") for v in merged[:1024].cpu().tolist()))
+    # e2e: pinned host query block -> H2D -> search -> all_gather -> OR -> D2H of the merged bitmap
+    hq = queries.cpu().pin_memory()
+    hb = torch.empty_like(bitmap, device="cpu").pin_memory()
+    sync_all()
+    e2e_steps = max(1, min(steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        queries.copy_(hq, non_blocking=True)
+        g = step()
+        hb.copy_(hdist.or_reduce(g), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    return {"n_db": n_db, "frames_per_video": fpv, "n_query": nq, "n_gpus": world, "shard_hashes_this_rank": nt,
+            "ms_per_step": ms_per_step, "pair_comparisons_per_s": float(n_db) * nq / (ms_per_step / 1e3),
+            "all_gather_us": gather_us, "all_gather_bytes_per_rank": int(bitmap.numel() * 4),
+            "all_gather_share_of_step": gather_us / 1e3 / ms_per_step,
+            "matches_all_ranks": int(total.item()), "first_32768_queries_flagged": flagged,
+            "collective": "nccl all_gather_into_tensor" if world > 1 else "none (single rank)",
+            "generator": "SURVEY 8d config 3: popcount-128 words + 1 % planted near-duplicates at distances 0..40",
+            "e2e": {"value": float(n_db) * nq * e2e_steps / e2e_s, "unit": "pair-comparisons/s",
+                    "h2d_bytes_per_step": nq * HASH_BYTES, "d2h_bytes_per_step": int(hb.numel() * 4), "steps": e2e_steps}}
+
+
+def luma_section(torch, dev_api, dev, local, args, sync_all, max_over_ranks, world) -> dict:
     """BASELINE's "512x512 luma frames" variant: 8-bit gray input, DEFINED as the RGB frame R=G=B=L (SURVEY.md note
-    a-1; one byte per pixel crosses PCIe instead of three).  Same kernels as the RGB24 path (kx_fused_jarosz2<1>)."""
+    a-1; one byte per pixel crosses PCIe instead of three).  Same kernels as the RGB24 path (kx_systolic_jarosz<1>).
+    Runs on every rank (whole-job rates, max over ranks)."""
     import ctypes as C
 
     from hydrus_video_deduplicator_b200 import _ffi
 
     n = min(args.batch, 2048)
-    g = torch.Generator(device=dev).manual_seed(4242)
+    g = torch.Generator(device=dev).manual_seed(4242 + local)
     gray = torch.randint(0, 256, (n, 512, 512), dtype=torch.uint8, device=dev, generator=g)
     for _ in range(2):
         dev_api.hash_frames(gray)
+    sync_all()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(5):
         h, q = dev_api.hash_frames(gray)
     b.record()
     torch.cuda.synchronize()
-    dev_rate = 5 * n / (a.elapsed_time(b) / 1e3)
+    dev_rate = world * 5 * n / (max_over_ranks(a.elapsed_time(b)) / 1e3)
     hg = torch.empty((n, 512, 512), dtype=torch.uint8, pin_memory=True)
     hg.copy_(gray)
     hh = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
@@ -522,36 +712,28 @@ def luma_section(torch, dev_api, dev, local, args) -> dict:
                                                              C.c_void_p(hh.data_ptr()), C.c_void_p(hq.data_ptr()), local))
 
     step()
+    sync_all()
     t0 = time.perf_counter()
     for _ in range(5):
         step()
-    e2e_rate = 5 * n / (time.perf_counter() - t0)
+    e2e_rate = world * 5 * n / max_over_ranks(time.perf_counter() - t0)
     rgb = gray[:4].unsqueeze(-1).expand(-1, -1, -1, 3).contiguous()
     same = bool(torch.equal(dev_api.hash_frames(rgb)[0], h[:4]) and torch.equal(hh[:4], h[:4].cpu()))
-    return {"frames_per_s_device_resident": dev_rate, "frames_per_s_e2e": e2e_rate, "frames": n,
-            "bytes_per_frame": 512 * 512, "equals_rgb_expansion": same,
-            "kernels": ("k1_luma_rowpass<1> + k2_colpass + k3_rowpass_dec + k4_colpass_finalize<false>"
-                        if os.environ.get("VPDQ_B200_PDQ_IMPL", "") in ("lines", "fused")
-                        else "kx_fused_jarosz2<1> + k5_finalize")}
+    return {"frames_per_s_device_resident": dev_rate, "frames_per_s_e2e": e2e_rate, "frames_per_rank": n, "n_gpus": world,
+            "bytes_per_frame": 512 * 512, "equals_rgb_expansion": same, "kernels": "kx_systolic_jarosz<1> + k5_finalize"}
 
 
 def hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args) -> dict:
-    """Streaming-scan GB/s (HBM-bound regime) and all-pairs comparisons/s on one GPU."""
+    """One GPU: streaming-scan GB/s (the HBM-bound regime) by resident query count, 1M x 1M all pairs, and both
+    kernels again on a video-like database whose match density is that of a real library."""
     from hydrus_video_deduplicator_b200 import _ffi
 
     out = {}
-    n_db = args.scan_hashes
-    db = device_hashes(torch, n_db, dev, seed=9)
-    fpv = 300
-    offsets = torch.arange(0, n_db + 1, fpv, dtype=torch.int64, device=dev)
-    if int(offsets[-1]) != n_db:
-        offsets = torch.cat([offsets, torch.tensor([n_db], dtype=torch.int64, device=dev)])
-    n_videos = offsets.numel() - 1
-    qmask = torch.zeros((n_videos,), dtype=torch.int64, device=dev)
-    scan = {}
     stream = torch.cuda.current_stream().cuda_stream
-    for nq in (1, 2, 4, 8, 16):
-        q = db[:nq].clone()
+
+    def time_scan(db, offsets, q):
+        n_db, nq, n_videos = db.shape[0], q.shape[0], offsets.numel() - 1
+        qmask = torch.zeros((n_videos,), dtype=torch.int64, device=dev)
 
         def run():
             _ffi.check(_ffi.lib().vpdq_b200_hamming_scan_dev(db.data_ptr(), n_db, offsets.data_ptr(), n_videos,
@@ -569,28 +751,47 @@ def hamming_section(torch, dev_api, dev, peak, peak_src, flush_l2, args) -> dict
             times.append(a.elapsed_time(b))
         ms = statistics.mean(times)
         gbs = n_db * HASH_BYTES / (ms / 1e3) / 1e9
-        scan[str(nq)] = {"ms": ms, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak,
-                         "pair_comparisons_per_s": n_db * nq / (ms / 1e3)}
+        return {"ms": ms, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak, "pair_comparisons_per_s": n_db * nq / (ms / 1e3),
+                "videos_hit": int((qmask != 0).sum())}
+
+    n_db, fpv = args.scan_hashes, 300
+    db = device_hashes(torch, n_db, dev, seed=9)
+    offsets = torch.arange(0, n_db + 1, fpv, dtype=torch.int64, device=dev)
+    if int(offsets[-1]) != n_db:
+        offsets = torch.cat([offsets, torch.tensor([n_db], dtype=torch.int64, device=dev)])
+    scan = {str(nq): time_scan(db, offsets, db[:nq].clone()) for nq in (1, 2, 4, 8, 16, 64)}
     out["scan"] = {"n_db": n_db, "db_bytes": n_db * HASH_BYTES, "frames_per_video": fpv, "by_n_query": scan,
                    "peak_GB/s": peak, "peak_source": peak_src, "algorithmic_bytes_per_hash": HASH_BYTES,
+                   "generator": "SURVEY 8d config 3",
                    "note": "DB (320 MB) exceeds L2 (126 MB): every launch streams it from HBM"}
-    # all pairs, 1M x 1M
+    del db
+
+    def time_pairs(h, reps=2):
+        n = h.shape[0]
+        dev_api.hamming_pairs(h[: n // 8], h, 31, skip_diagonal=True, capacity=1, want_bitmap=True)
+        times, found = [], 0
+        for _ in range(reps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            found, _, _ = dev_api.hamming_pairs(h, h, 31, skip_diagonal=True, capacity=1, want_bitmap=True)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        ms = statistics.mean(times)
+        return {"n_q": n, "n_t": n, "ms": ms, "pair_comparisons_per_s": float(n) * n / (ms / 1e3), "matches": int(found)}
+
     n = args.pairs_hashes
-    h = device_hashes(torch, n, dev, seed=10)
-    for _ in range(1):
-        dev_api.hamming_pairs(h[: n // 8], h, 31, skip_diagonal=True)
-    times, found = [], 0
-    for _ in range(2):
-        flush_l2()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        found, _, _ = dev_api.hamming_pairs(h, h, 31, skip_diagonal=True)
-        b.record()
-        torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    ms = statistics.mean(times)
-    out["all_pairs"] = {"n_q": n, "n_t": n, "ms": ms, "pair_comparisons_per_s": float(n) * n / (ms / 1e3),
-                        "matches": int(found), "bound": "POPC issue (DB is L2 resident; compulsory HBM bytes = 64 MB)"}
+    out["all_pairs"] = time_pairs(device_hashes(torch, n, dev, seed=10))
+    out["all_pairs"]["bound"] = "POPC issue (DB is L2 resident; compulsory HBM bytes = 64 MB)"
+    out["all_pairs"]["generator"] = "SURVEY 8d config 3"
+    # the same kernels where matches are dense: 300-frame random-walk videos, 5 % duplicated videos
+    vdb, voff = device_video_hashes(torch, n_db // fpv, fpv, dev, seed=11)
+    vscan = {str(nq): time_scan(vdb, voff, vdb[1000 * fpv:1000 * fpv + nq].clone()) for nq in (1, 8, 64)}
+    vpairs = time_pairs(vdb[: (n // fpv) * fpv].contiguous(), reps=1)
+    out["video_like_db"] = {"what": "random-walk videos (adjacent frames <= 16 bits apart), 5 % duplicate videos",
+                            "scan_n_db": int(vdb.shape[0]), "scan_by_n_query": vscan, "all_pairs": vpairs,
+                            "matches_per_query_frame": vpairs["matches"] / max(1, vpairs["n_q"])}
     return out
 
 
@@ -613,8 +814,10 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--scan-hashes", type=int, default=10_000_000)
     ap.add_argument("--pairs-hashes", type=int, default=1 << 20)
-    ap.add_argument("--shard-hashes", type=int, default=1_250_000)
+    ap.add_argument("--shard-db-hashes", type=int, default=10_000_000, help="the FIXED database sharded over the ranks")
+    ap.add_argument("--shard-steps", type=int, default=3)
     ap.add_argument("--query-block", type=int, default=262_144)
+    ap.add_argument("--no-hasher-api", action="store_true")
     ap.add_argument("--no-hamming", action="store_true")
     ap.add_argument("--no-luma", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -50,8 +50,6 @@ PROTOTYPES = {
     "vpdq_b200_kernel_launches": (C.c_int, [C.POINTER(C.c_uint64)]),
     "vpdq_b200_debug_flags": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "vpdq_b200_debug_force_timeout": (C.c_int, [C.c_int, C.c_int]),
-    "vpdq_b200_set_pdq_impl": (C.c_int, [C.c_int]),
-    "vpdq_b200_get_pdq_impl": (C.c_int, []),
     "vpdq_b200_dct_matrix": (C.c_int, [_f32p]),
     "vpdq_b200_pdq_scratch_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
     "vpdq_b200_pdq_hash_frames_dev": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp,
@@ -69,11 +67,14 @@ PROTOTYPES = {
     "vpdq_b200_hasher_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _i64p, _vp, _vp]),
     "vpdq_b200_hasher_destroy": (C.c_int, [_vp]),
     "vpdq_b200_hamming_scan_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "vpdq_b200_hamming_scan_multi_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "vpdq_b200_video_match_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, _vp]),
     "vpdq_b200_hamming_pairs_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, C.c_int64,
                                               _vp, _vp]),
     "vpdq_b200_match_hash_host": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "vpdq_b200_db_create": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, C.c_int64, C.POINTER(_vp)]),
     "vpdq_b200_db_search": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "vpdq_b200_db_search_radius": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int64, _i64p]),
     "vpdq_b200_db_destroy": (C.c_int, [_vp]),
     "vpdq_b200_search_host": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
 }
@@ -119,19 +120,6 @@ def kernel_launches() -> int:
     n = C.c_uint64(0)
     check(lib().vpdq_b200_kernel_launches(C.byref(n)))
     return int(n.value)
-
-
-PDQ_IMPLS = {"lines": 0, "fused": 1, "fused2": 2, "systolic": 3}
-
-
-def set_pdq_impl(name: str) -> None:
-    """A/B switch between the bit-identical CUDA pipelines for RGB24 frames (default "fused2")."""
-    check(lib().vpdq_b200_set_pdq_impl(PDQ_IMPLS[name]))
-
-
-def get_pdq_impl() -> str:
-    v = lib().vpdq_b200_get_pdq_impl()
-    return {v: k for k, v in PDQ_IMPLS.items()}[v]
 
 
 def debug_flags(device: int = 0) -> int:

@@ -12,5 +12,5 @@ if [[ "${VPDQ_PTXAS_V:-0}" == "1" ]]; then FLAGS+=(-Xptxas -v); fi
 # dev: extra -D switches and an alternative output path (tools/kx_libs.py times several builds side by side)
 if [[ -n "${VPDQ_EXTRA_DEFS:-}" ]]; then FLAGS+=(${VPDQ_EXTRA_DEFS}); fi
 OUT=${VPDQ_OUT:-$OUT}
-"$NVCC" "${FLAGS[@]}" -o "$OUT" pdq_kernels.cu pdq_fused.cu pdq_fused2.cu pdq_systolic.cu resize_kernels.cu hamming_kernels.cu capi.cu
+"$NVCC" "${FLAGS[@]}" -o "$OUT" pdq_kernels.cu pdq_systolic.cu resize_kernels.cu hamming_kernels.cu capi.cu
 echo "built $(realpath "$OUT")"

@@ -105,7 +105,7 @@ struct CudaDev {
         memset(h_flags, 0, 4 * sizeof(int));
         VPDQ_CUDA(cudaMalloc(&d_hash, n * 32));
         VPDQ_CUDA(cudaMalloc(&d_quality, n * sizeof(int32_t)));
-        scratch_bytes = n * fused_scratch_per_frame();
+        scratch_bytes = pdq_scratch_bytes((int64_t)n);
         VPDQ_CUDA(cudaMalloc(&d_scratch, scratch_bytes));
         *hf = h_frames;
         *df = d_frames;
@@ -150,9 +150,8 @@ struct CudaDev {
         return true;
     }
     int launch_status() {
-        if (h_flags[0] | h_flags[1] | h_flags[2]) {
-            set_error("a TMA copy inside the PDQ kernel never completed (flags %d %d %d): results invalid", h_flags[0],
-                      h_flags[1], h_flags[2]);
+        if (h_flags[0]) {
+            set_error("a TMA copy inside the PDQ kernel never completed: results invalid");
             return VPDQ_B200_ERR_CUDA;
         }
         return VPDQ_B200_OK;
@@ -240,14 +239,7 @@ int vpdq_b200_debug_flags(int device, int* flags) {
     DeviceGuard g(device);
     if (g.rc) return g.rc;
     VPDQ_CUDA(cudaDeviceSynchronize());
-    int f1 = 0, f2 = 0, f3 = 0;
-    int rc = fused_debug_flags(&f1);
-    if (rc) return rc;
-    rc = fused2_debug_flags(&f2);
-    if (rc) return rc;
-    rc = systolic_debug_flags(&f3);
-    if (rc) return rc;
-    *flags = f1 | f2 | f3;
+    return systolic_debug_flags(flags);
     return VPDQ_B200_OK;
 }
 
@@ -258,8 +250,6 @@ int vpdq_b200_debug_force_timeout(int device, int value) {
     return pdq_force_timeout_flags(value);
 }
 
-int vpdq_b200_set_pdq_impl(int impl) { return pdq_set_impl(impl); }
-int vpdq_b200_get_pdq_impl(void) { return pdq_impl(); }
 
 int vpdq_b200_device_count(int* count) {
     if (!count) return VPDQ_B200_ERR_INVALID;
@@ -407,10 +397,7 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
     HostPipe& p = g_pipes[dev];
     std::lock_guard<std::mutex> lk(p.mu);
     const int64_t chunk = n_frames < kHostChunk ? n_frames : kHostChunk;
-    const size_t scr = (size_t)kHostChunk * fused_scratch_per_frame() > pdq_scratch_bytes(1)
-                           ? (size_t)kHostChunk * fused_scratch_per_frame()
-                           : pdq_scratch_bytes(1);
-    rc = host_pipe_prepare(p, (size_t)kHostChunk * (size_t)kPlane * 3, pdq_impl() == 0 ? pdq_scratch_bytes(kHostChunk) : scr);
+    rc = host_pipe_prepare(p, (size_t)kHostChunk * (size_t)kPlane * 3, pdq_scratch_bytes(kHostChunk));
     if (rc) return rc;
     memset(p.h_flags, 0, kHostStages * 4 * sizeof(int));
     int c = 0;
@@ -433,7 +420,7 @@ int vpdq_b200_pdq_hash_frames_host(const uint8_t* h_frames, int channels, int64_
         if (e != cudaSuccess && rc == VPDQ_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
     if (rc == VPDQ_B200_OK)
-        for (int i = 0; i < kHostStages * 4; ++i)
+        for (int i = 0; i < kHostStages * 4; i += 4)
             if (p.h_flags[i]) {
                 set_error("a TMA copy inside the PDQ kernel never completed: results invalid");
                 rc = VPDQ_B200_ERR_CUDA;
@@ -450,9 +437,7 @@ int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int widt
         set_error("pdq_jarosz: NULL output or pointers not 16-byte aligned");
         return VPDQ_B200_ERR_INVALID;
     }
-    return pdq_impl() == 1   ? fused_jarosz_launch(d_frames, n_frames, d_a64, (cudaStream_t)stream)
-           : pdq_impl() == 2 ? fused2_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream)
-                             : systolic_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream);
+    return systolic_jarosz_launch(d_frames, 3, n_frames, d_a64, (cudaStream_t)stream);
 }
 
 int vpdq_b200_point_resize_dev(const uint8_t* d_src, int64_t n_frames, int src_height, int src_width, uint8_t* d_dst,
@@ -599,6 +584,43 @@ int vpdq_b200_hamming_scan_dev(const uint64_t* d_db, int64_t n_db, const int64_t
                                (cudaStream_t)stream);
 }
 
+int vpdq_b200_hamming_scan_multi_dev(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets, int64_t n_videos,
+                                     const uint64_t* d_query, const int32_t* d_chunk_rows, int n_chunks, int tolerance,
+                                     uint64_t* d_qmask, void* stream) {
+    if (n_db < 0 || n_videos < 0 || n_chunks < 0 || tolerance < 0) {
+        set_error("hamming_scan_multi: invalid sizes");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (n_db == 0 || n_chunks == 0) return VPDQ_B200_OK;
+    if (!d_db || !d_query || !d_chunk_rows || !d_qmask || (!d_offsets && n_videos != n_db) || (d_offsets && n_videos < 1)) {
+        set_error("hamming_scan_multi: NULL pointer or n_videos inconsistent with offsets");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (((uintptr_t)d_db & 31) || ((uintptr_t)d_query & 31)) {
+        set_error("hamming_scan_multi: db and query must be 32-byte aligned");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return hamming_scan_multi_launch(d_db, n_db, d_offsets, n_videos, d_query, d_chunk_rows, n_chunks, tolerance, d_qmask,
+                                     (cudaStream_t)stream);
+}
+
+int vpdq_b200_video_match_dev(const uint64_t* d_qmask, int64_t n_videos, const int32_t* d_qv_chunks,
+                              const int32_t* d_qv_frames, int n_qvideos, int max_distance, int32_t* d_matched,
+                              int32_t* d_rows, int64_t cap, unsigned long long* d_count, void* stream) {
+    if (n_videos < 0 || n_qvideos < 0 || cap < 0) {
+        set_error("video_match: invalid sizes");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    if (n_videos == 0 || n_qvideos == 0) return VPDQ_B200_OK;
+    if (!d_qmask || !d_qv_chunks || !d_qv_frames || (!d_matched && !d_rows) || (d_rows && !d_count) ||
+        ((uintptr_t)d_rows & 15)) {
+        set_error("video_match: NULL pointer (or rows not 16-byte aligned)");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    return video_reduce_launch(d_qmask, n_videos, d_qv_chunks, d_qv_frames, n_qvideos, max_distance, d_matched, d_rows,
+                               cap, d_count, (cudaStream_t)stream);
+}
+
 int vpdq_b200_hamming_pairs_dev(const uint64_t* d_q, int64_t n_q, const uint64_t* d_t, int64_t n_t, int tolerance,
                                 int skip_diagonal, uint32_t* d_any, uint64_t* d_pairs, int64_t cap,
                                 unsigned long long* d_count, void* stream) {
@@ -629,9 +651,16 @@ struct vpdq_b200_db {
     int64_t n_db = 0, n_videos = 0;
     uint64_t* d_db = nullptr;
     int64_t* d_offsets = nullptr;
-    uint64_t* d_qmask = nullptr;  // [n_videos]
-    uint64_t* d_query = nullptr;  // [64][4]
-    uint64_t* h_qmask = nullptr;  // pinned
+    // per-search workspace, grown on demand and kept
+    uint64_t* d_query = nullptr;      // [q_cap][4]
+    int32_t* d_meta = nullptr;        // chunk rows [c_cap + 1] | qv_chunks [2] | qv_frames [1]
+    uint64_t* d_qmask = nullptr;      // [c_cap][n_videos]
+    int32_t* d_matched = nullptr;     // [n_videos]
+    int32_t* d_rows = nullptr;        // [n_videos][4]
+    unsigned long long* d_count = nullptr;
+    int32_t* h_meta = nullptr;        // pinned mirror of d_meta
+    unsigned long long* h_count = nullptr;  // pinned
+    int64_t q_cap = 0, c_cap = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
 };
@@ -639,11 +668,71 @@ struct vpdq_b200_db {
 static void db_free(vpdq_b200_db* db) {
     if (db->d_db) cudaFree(db->d_db);
     if (db->d_offsets) cudaFree(db->d_offsets);
-    if (db->d_qmask) cudaFree(db->d_qmask);
     if (db->d_query) cudaFree(db->d_query);
-    if (db->h_qmask) cudaFreeHost(db->h_qmask);
+    if (db->d_meta) cudaFree(db->d_meta);
+    if (db->d_qmask) cudaFree(db->d_qmask);
+    if (db->d_matched) cudaFree(db->d_matched);
+    if (db->d_rows) cudaFree(db->d_rows);
+    if (db->d_count) cudaFree(db->d_count);
+    if (db->h_meta) cudaFreeHost(db->h_meta);
+    if (db->h_count) cudaFreeHost(db->h_count);
     if (db->stream) cudaStreamDestroy(db->stream);
     delete db;
+}
+
+// grow the per-search workspace for a query of n_query frames
+static int db_reserve(vpdq_b200_db* db, int64_t n_query) {
+    const int64_t n_chunks = (n_query + 63) / 64;
+    const int64_t V = db->n_videos > 0 ? db->n_videos : 1;
+    if (n_query > db->q_cap) {
+        int64_t cap = db->q_cap ? db->q_cap : 64;
+        while (cap < n_query) cap *= 2;
+        if (db->d_query) VPDQ_CUDA(cudaFree(db->d_query));
+        db->d_query = nullptr;
+        db->q_cap = 0;
+        VPDQ_CUDA(cudaMalloc(&db->d_query, (size_t)cap * 32));
+        db->q_cap = cap;
+    }
+    if (n_chunks > db->c_cap) {
+        int64_t cap = db->c_cap ? db->c_cap : 1;
+        while (cap < n_chunks) cap *= 2;
+        if (db->d_qmask) VPDQ_CUDA(cudaFree(db->d_qmask));
+        if (db->d_meta) VPDQ_CUDA(cudaFree(db->d_meta));
+        if (db->h_meta) VPDQ_CUDA(cudaFreeHost(db->h_meta));
+        db->d_qmask = nullptr;
+        db->d_meta = nullptr;
+        db->h_meta = nullptr;
+        db->c_cap = 0;
+        VPDQ_CUDA(cudaMalloc(&db->d_qmask, (size_t)cap * V * sizeof(uint64_t)));
+        VPDQ_CUDA(cudaMalloc(&db->d_meta, (size_t)(cap + 4) * sizeof(int32_t)));
+        VPDQ_CUDA(cudaHostAlloc(&db->h_meta, (size_t)(cap + 4) * sizeof(int32_t), cudaHostAllocDefault));
+        db->c_cap = cap;
+    }
+    return VPDQ_B200_OK;
+}
+
+// upload the query, scan every 64-frame chunk of it against the whole DB in ONE launch and reduce the per-chunk
+// masks to per-video matched-frame counts on the device; leaves the stream un-synchronised
+static int db_scan_and_reduce(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_query, int tolerance, int max_distance,
+                              bool want_dense, bool want_rows) {
+    int rc = db_reserve(db, n_query);
+    if (rc) return rc;
+    const int n_chunks = (int)((n_query + 63) / 64);
+    int32_t* m = db->h_meta;
+    for (int c = 0; c <= n_chunks; ++c) m[c] = (int32_t)((int64_t)c * 64 < n_query ? (int64_t)c * 64 : n_query);
+    m[n_chunks + 1] = 0;               // qv_chunks[0]
+    m[n_chunks + 2] = n_chunks;        // qv_chunks[1]
+    m[n_chunks + 3] = (int32_t)n_query;  // qv_frames[0]
+    VPDQ_CUDA(cudaMemcpyAsync(db->d_query, h_query, (size_t)n_query * 32, cudaMemcpyHostToDevice, db->stream));
+    VPDQ_CUDA(cudaMemcpyAsync(db->d_meta, m, (size_t)(n_chunks + 4) * sizeof(int32_t), cudaMemcpyHostToDevice, db->stream));
+    VPDQ_CUDA(cudaMemsetAsync(db->d_qmask, 0, (size_t)n_chunks * db->n_videos * sizeof(uint64_t), db->stream));
+    if (want_rows) VPDQ_CUDA(cudaMemsetAsync(db->d_count, 0, sizeof(unsigned long long), db->stream));
+    rc = hamming_scan_multi_launch(db->d_db, db->n_db, db->d_offsets, db->n_videos, db->d_query, db->d_meta, n_chunks,
+                                   tolerance, db->d_qmask, db->stream);
+    if (rc) return rc;
+    return video_reduce_launch(db->d_qmask, db->n_videos, db->d_meta + n_chunks + 1, db->d_meta + n_chunks + 3, 1,
+                               max_distance, want_dense ? db->d_matched : nullptr, want_rows ? db->d_rows : nullptr,
+                               db->n_videos, db->d_count, db->stream);
 }
 
 extern "C" {
@@ -676,14 +765,15 @@ int vpdq_b200_db_create(int device, const uint8_t* h_db, int64_t n_db, const int
     if (!db) return VPDQ_B200_ERR_NOMEM;
     db->n_db = n_db;
     db->n_videos = n_videos;
+    const size_t V = (size_t)(n_videos > 0 ? n_videos : 1);
     cudaError_t e = cudaGetDevice(&db->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&db->d_db, (size_t)(n_db > 0 ? n_db : 1) * 32);
     if (e == cudaSuccess) e = cudaMalloc(&db->d_offsets, (size_t)(n_videos + 1) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&db->d_qmask, (size_t)(n_videos > 0 ? n_videos : 1) * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&db->d_query, 64 * 32);
-    if (e == cudaSuccess)
-        e = cudaHostAlloc(&db->h_qmask, (size_t)(n_videos > 0 ? n_videos : 1) * sizeof(uint64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_matched, V * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_rows, V * 4 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_count, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc(&db->h_count, sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess && n_db > 0)
         e = cudaMemcpyAsync(db->d_db, h_db, (size_t)n_db * 32, cudaMemcpyHostToDevice, db->stream);
     if (e == cudaSuccess && n_videos > 0)
@@ -705,21 +795,47 @@ int vpdq_b200_db_search(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_quer
         return VPDQ_B200_ERR_INVALID;
     }
     std::lock_guard<std::mutex> lk(db->mu);
-    for (int64_t v = 0; v < db->n_videos; ++v) h_matched[v] = 0;
+    if (db->n_db == 0 || n_query == 0 || db->n_videos == 0) {
+        for (int64_t v = 0; v < db->n_videos; ++v) h_matched[v] = 0;
+        return VPDQ_B200_OK;
+    }
+    DeviceGuard g(db->device);
+    if (g.rc) return g.rc;
+    // any number of query frames: one upload, one scan launch over all 64-frame chunks, the popcounts on the device,
+    // one read-back, one synchronisation
+    int rc = db_scan_and_reduce(db, h_query, n_query, tolerance, 0, true, false);
+    if (rc) return rc;
+    VPDQ_CUDA(cudaMemcpyAsync(h_matched, db->d_matched, (size_t)db->n_videos * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              db->stream));
+    VPDQ_CUDA(cudaStreamSynchronize(db->stream));
+    return VPDQ_B200_OK;
+}
+
+int vpdq_b200_db_search_radius(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_query, int tolerance, int max_distance,
+                               int32_t* h_rows, int64_t cap, int64_t* n_rows) {
+    if (!db || !n_rows || n_query < 0 || tolerance < 0 || cap < 0 || (n_query > 0 && !h_query) || (cap > 0 && !h_rows)) {
+        set_error("db_search_radius: invalid argument");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    *n_rows = 0;
+    std::lock_guard<std::mutex> lk(db->mu);
     if (db->n_db == 0 || n_query == 0 || db->n_videos == 0) return VPDQ_B200_OK;
     DeviceGuard g(db->device);
     if (g.rc) return g.rc;
-    for (int64_t q0 = 0; q0 < n_query; q0 += 64) {
-        const int nq = (int)(n_query - q0 < 64 ? n_query - q0 : 64);
-        VPDQ_CUDA(cudaMemcpyAsync(db->d_query, h_query + q0 * 32, (size_t)nq * 32, cudaMemcpyHostToDevice, db->stream));
-        VPDQ_CUDA(cudaMemsetAsync(db->d_qmask, 0, (size_t)db->n_videos * sizeof(uint64_t), db->stream));
-        int rc = hamming_scan_launch(db->d_db, db->n_db, db->d_offsets, db->n_videos, db->d_query, nq, tolerance,
-                                     db->d_qmask, nullptr, db->stream);
-        if (rc) return rc;
-        VPDQ_CUDA(cudaMemcpyAsync(db->h_qmask, db->d_qmask, (size_t)db->n_videos * sizeof(uint64_t),
-                                  cudaMemcpyDeviceToHost, db->stream));
+    int rc = db_scan_and_reduce(db, h_query, n_query, tolerance, max_distance, false, true);
+    if (rc) return rc;
+    VPDQ_CUDA(cudaMemcpyAsync(db->h_count, db->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+    VPDQ_CUDA(cudaStreamSynchronize(db->stream));
+    const int64_t n = (int64_t)*db->h_count;  // <= n_videos = the capacity of d_rows
+    *n_rows = n;
+    const int64_t take = n < cap ? n : cap;
+    if (take > 0) {
+        VPDQ_CUDA(cudaMemcpyAsync(h_rows, db->d_rows, (size_t)take * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, db->stream));
         VPDQ_CUDA(cudaStreamSynchronize(db->stream));
-        for (int64_t v = 0; v < db->n_videos; ++v) h_matched[v] += __builtin_popcountll(db->h_qmask[v]);
+    }
+    if (n > cap) {
+        set_error("db_search_radius: %lld videos within the radius but capacity is %lld", (long long)n, (long long)cap);
+        return VPDQ_B200_ERR_OVERFLOW;
     }
     return VPDQ_B200_OK;
 }
@@ -744,18 +860,18 @@ int vpdq_b200_search_host(const uint8_t* h_db, int64_t n_db, const int64_t* h_of
 
 // Per-device scratch of vpdq_b200_match_hash_host, kept between calls (grow-only): the reference calls
 // matchHash once per pair (test_benchmark_vpdqpy.py:49-73), so per-call cudaMalloc / several small copies would
-// dominate.  One pinned staging block [mask | offsets | 64 query hashes | targets] goes down in ONE copy (the
-// zeroed mask word travels with it), one kernel runs, 8 bytes come back.
+// dominate.  One pinned staging block [chunk masks | chunk rows | offsets | queries | targets] goes down in ONE copy
+// (the zeroed masks travel with it), ONE kernel scans every 64-frame chunk of the query, the masks come back.
 namespace {
 struct MatchScratch {
     cudaStream_t stream = nullptr;
     uint8_t* h_blk = nullptr;  // pinned
     uint8_t* d_blk = nullptr;
-    size_t t_cap = 0;          // target capacity in hashes
+    size_t cap_bytes = 0;
     std::mutex mu;
 };
-constexpr size_t kMaskOff = 0, kOffOff = 32, kQOff = 64, kTOff = 64 + 64 * 32;
 MatchScratch g_match[64];
+inline size_t align32(size_t x) { return (x + 31) & ~(size_t)31; }
 }  // namespace
 
 int vpdq_b200_match_hash_host(const uint8_t* h_q, int64_t n_q, const uint8_t* h_t, int64_t n_t, int tolerance,
@@ -781,38 +897,42 @@ int vpdq_b200_match_hash_host(const uint8_t* h_q, int64_t n_q, const uint8_t* h_
     MatchScratch& m = g_match[dev];
     std::lock_guard<std::mutex> lk(m.mu);
     if (!m.stream) VPDQ_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
-    if ((size_t)n_t > m.t_cap) {
+    const int64_t n_chunks = (n_q + 63) / 64;
+    // layout (all 32-byte aligned): masks [n_chunks] u64 | chunk rows [n_chunks + 1] i32 | offsets [2] i64 | q | t
+    const size_t off_rows = align32((size_t)n_chunks * 8), off_off = off_rows + align32((size_t)(n_chunks + 1) * 4),
+                 off_q = off_off + 32, off_t = off_q + (size_t)n_q * 32, total = off_t + (size_t)n_t * 32;
+    if (total > m.cap_bytes) {
         if (m.d_blk) VPDQ_CUDA(cudaFree(m.d_blk));
         if (m.h_blk) VPDQ_CUDA(cudaFreeHost(m.h_blk));
         m.d_blk = nullptr;
         m.h_blk = nullptr;
-        m.t_cap = 0;
-        size_t cap = 1024;
-        while (cap < (size_t)n_t) cap *= 2;
-        VPDQ_CUDA(cudaMalloc(&m.d_blk, kTOff + cap * 32));
-        VPDQ_CUDA(cudaHostAlloc(&m.h_blk, kTOff + cap * 32, cudaHostAllocDefault));
-        m.t_cap = cap;
+        m.cap_bytes = 0;
+        size_t cap = 65536;
+        while (cap < total) cap *= 2;
+        VPDQ_CUDA(cudaMalloc(&m.d_blk, cap));
+        VPDQ_CUDA(cudaHostAlloc(&m.h_blk, cap, cudaHostAllocDefault));
+        m.cap_bytes = cap;
     }
+    memset(m.h_blk, 0, off_rows);
+    int32_t* rows = reinterpret_cast<int32_t*>(m.h_blk + off_rows);
+    for (int64_t c = 0; c <= n_chunks; ++c) rows[c] = (int32_t)(c * 64 < n_q ? c * 64 : n_q);
     const int64_t off[2] = {0, n_t};
-    memcpy(m.h_blk + kOffOff, off, sizeof off);
-    memcpy(m.h_blk + kTOff, h_t, (size_t)n_t * 32);
+    memcpy(m.h_blk + off_off, off, sizeof off);
+    memcpy(m.h_blk + off_q, h_q, (size_t)n_q * 32);
+    memcpy(m.h_blk + off_t, h_t, (size_t)n_t * 32);
+    VPDQ_CUDA(cudaMemcpyAsync(m.d_blk, m.h_blk, total, cudaMemcpyHostToDevice, m.stream));
+    int rc = hamming_scan_multi_launch(reinterpret_cast<const uint64_t*>(m.d_blk + off_t), n_t,
+                                       reinterpret_cast<const int64_t*>(m.d_blk + off_off), 1,
+                                       reinterpret_cast<const uint64_t*>(m.d_blk + off_q),
+                                       reinterpret_cast<const int32_t*>(m.d_blk + off_rows), (int)n_chunks, tolerance,
+                                       reinterpret_cast<uint64_t*>(m.d_blk), m.stream);
+    if (rc) return rc;
+    VPDQ_CUDA(cudaMemcpyAsync(m.h_blk, m.d_blk, (size_t)n_chunks * 8, cudaMemcpyDeviceToHost, m.stream));
+    VPDQ_CUDA(cudaStreamSynchronize(m.stream));
     int64_t matched = 0;
-    for (int64_t q0 = 0; q0 < n_q; q0 += 64) {
-        const int nq = (int)(n_q - q0 < 64 ? n_q - q0 : 64);
-        memset(m.h_blk + kMaskOff, 0, 8);
-        memcpy(m.h_blk + kQOff, h_q + q0 * 32, (size_t)nq * 32);
-        // first chunk: everything incl. the targets; later chunks: mask + offsets + queries only
-        const size_t bytes = q0 == 0 ? kTOff + (size_t)n_t * 32 : kTOff;
-        VPDQ_CUDA(cudaMemcpyAsync(m.d_blk, m.h_blk, bytes, cudaMemcpyHostToDevice, m.stream));
-        int rc = hamming_scan_launch(reinterpret_cast<const uint64_t*>(m.d_blk + kTOff), n_t,
-                                     reinterpret_cast<const int64_t*>(m.d_blk + kOffOff), 1,
-                                     reinterpret_cast<const uint64_t*>(m.d_blk + kQOff), nq, tolerance,
-                                     reinterpret_cast<uint64_t*>(m.d_blk + kMaskOff), nullptr, m.stream);
-        if (rc) return rc;
-        VPDQ_CUDA(cudaMemcpyAsync(m.h_blk + kMaskOff, m.d_blk + kMaskOff, 8, cudaMemcpyDeviceToHost, m.stream));
-        VPDQ_CUDA(cudaStreamSynchronize(m.stream));
+    for (int64_t c = 0; c < n_chunks; ++c) {
         uint64_t mask;
-        memcpy(&mask, m.h_blk + kMaskOff, 8);
+        memcpy(&mask, m.h_blk + c * 8, 8);
         matched += __builtin_popcountll(mask);
     }
     *similarity = (100.0 * (double)matched) / (double)n_q;

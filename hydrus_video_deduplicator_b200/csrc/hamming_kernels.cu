@@ -68,11 +68,21 @@ __device__ __forceinline__ int prefix96_distance(const uint32_t (&q)[3], const u
 constexpr int kScanThreads = 256;
 constexpr int kScanUnroll = 2;
 
+// chunk_rows == nullptr: ONE chunk = query rows [0, n_query) (the single-video call).  Otherwise blockIdx.y = chunk c:
+// query rows chunk_rows[c] .. chunk_rows[c+1] - 1 (<= 64 of them), results in qmask[c][n_videos] -- many query videos
+// (or the pieces of a long one) against the database in one launch.
 __global__ void __launch_bounds__(kScanThreads)
     k_hamming_scan(const uint64_t* __restrict__ db, int64_t n_db, const int64_t* __restrict__ offsets,
-                   int64_t n_videos, const uint64_t* __restrict__ query, int n_query, int tol,
-                   unsigned long long* __restrict__ qmask, int32_t* __restrict__ tcount) {
+                   int64_t n_videos, const uint64_t* __restrict__ query, int n_query,
+                   const int32_t* __restrict__ chunk_rows, int tol, unsigned long long* __restrict__ qmask,
+                   int32_t* __restrict__ tcount) {
     __shared__ uint4 q_s[64 * 2];
+    if (chunk_rows) {
+        const int r0 = __ldg(chunk_rows + blockIdx.y);
+        n_query = __ldg(chunk_rows + blockIdx.y + 1) - r0;
+        query += 4 * (int64_t)r0;
+        qmask += (int64_t)blockIdx.y * n_videos;
+    }
     for (int e = threadIdx.x; e < n_query * 2; e += kScanThreads)
         q_s[e] = __ldg(reinterpret_cast<const uint4*>(query) + e);
     __syncthreads();
@@ -134,8 +144,85 @@ int hamming_scan_launch(const uint64_t* d_db, int64_t n_db, const int64_t* d_off
     const int64_t n_tiles = (n_db + kTile - 1) / kTile;
     const int64_t max_grid = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM, persistent
     const unsigned grid = (unsigned)(n_tiles < max_grid ? n_tiles : max_grid);
-    k_hamming_scan<<<grid, kScanThreads, 0, stream>>>(d_db, n_db, d_offsets, n_videos, d_query, n_query, tol,
+    k_hamming_scan<<<grid, kScanThreads, 0, stream>>>(d_db, n_db, d_offsets, n_videos, d_query, n_query, nullptr, tol,
                                                       reinterpret_cast<unsigned long long*>(d_qmask), d_tcount);
+    g_launches += 1;
+    VPDQ_CUDA(cudaGetLastError());
+    return VPDQ_B200_OK;
+}
+
+int hamming_scan_multi_launch(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets, int64_t n_videos,
+                              const uint64_t* d_query, const int32_t* d_chunk_rows, int n_chunks, int tol,
+                              uint64_t* d_qmask, cudaStream_t stream) {
+    if (n_db == 0 || n_chunks == 0) return VPDQ_B200_OK;
+    int dev = 0, sms = 148;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    VPDQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t kTile = (int64_t)kScanThreads * kScanUnroll;
+    const int64_t n_tiles = (n_db + kTile - 1) / kTile;
+    // the whole grid (all chunks) fills the machine a few times over; a chunk's CTAs stride over the DB tiles
+    int64_t per_chunk = ((int64_t)sms * 8 + n_chunks - 1) / n_chunks;
+    if (per_chunk > n_tiles) per_chunk = n_tiles;
+    if (per_chunk < 1) per_chunk = 1;
+    for (int c0 = 0; c0 < n_chunks; c0 += 65535) {  // grid.y limit
+        const int nc = n_chunks - c0 < 65535 ? n_chunks - c0 : 65535;
+        dim3 grid((unsigned)per_chunk, (unsigned)nc);
+        k_hamming_scan<<<grid, kScanThreads, 0, stream>>>(d_db, n_db, d_offsets, n_videos, d_query, 0, d_chunk_rows + c0, tol,
+                                                          reinterpret_cast<unsigned long long*>(d_qmask) + (int64_t)c0 * n_videos,
+                                                          nullptr);
+        g_launches += 1;
+    }
+    VPDQ_CUDA(cudaGetLastError());
+    return VPDQ_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// video-level reduce: per-chunk frame masks -> matchHash numerators -> distances -> compact list
+// ---------------------------------------------------------------------------------------------------
+// The reference scores a pair of videos as  similarity = 100 * |{query frames with >= 1 match}| / n_query_frames  and
+// distance = (100 - int(similarity)) + 1  (vpdqpy.py:56, db/vptree.py:22-31).  After a (multi-chunk) scan, bit i of
+// qmask[c][v] says that query frame i of chunk c has a match in target video v; query video q owns the chunks
+// qv_chunks[q] .. qv_chunks[q+1] - 1 and has qv_frames[q] frames.  One thread per target video:
+//   matched(q, v) = sum over q's chunks of popcount(qmask[c][v])      (distinct query frames by construction)
+// written densely (matched_dense[q][v]) and / or appended as (q, v, matched, distance) rows when matched > 0 and
+// distance <= max_distance (max_distance <= 0: no distance filter).  floor(100 m / n) in integers equals the
+// reference's int(100.0 * m / n): a quotient that is not an integer is at least 1 / n away from one.
+__global__ void __launch_bounds__(256)
+    k_video_reduce(const unsigned long long* __restrict__ qmask, int64_t n_videos, const int32_t* __restrict__ qv_chunks,
+                   const int32_t* __restrict__ qv_frames, int n_qvideos, int max_distance,
+                   int32_t* __restrict__ matched_dense, int4* __restrict__ rows, long long cap,
+                   unsigned long long* __restrict__ count) {
+    const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (v >= n_videos) return;
+    for (int q = blockIdx.y; q < n_qvideos; q += gridDim.y) {
+        const int c0 = __ldg(qv_chunks + q), c1 = __ldg(qv_chunks + q + 1);
+        int m = 0;
+        for (int c = c0; c < c1; ++c) m += __popcll(__ldg(qmask + (int64_t)c * n_videos + v));
+        if (matched_dense) matched_dense[(int64_t)q * n_videos + v] = m;
+        if (rows && m > 0) {
+            const int n = __ldg(qv_frames + q);
+            const int dist = n > 0 ? (100 - (100 * m) / n) + 1 : 101;
+            if (max_distance <= 0 || dist <= max_distance) {
+                const unsigned long long pos = atomicAdd(count, 1ull);
+                if ((long long)pos < cap) rows[pos] = make_int4(q, (int)v, m, dist);
+            }
+        }
+    }
+}
+
+int video_reduce_launch(const uint64_t* d_qmask, int64_t n_videos, const int32_t* d_qv_chunks, const int32_t* d_qv_frames,
+                        int n_qvideos, int max_distance, int32_t* d_matched_dense, int32_t* d_rows, int64_t cap,
+                        unsigned long long* d_count, cudaStream_t stream) {
+    if (n_videos == 0 || n_qvideos == 0) return VPDQ_B200_OK;
+    const int64_t gx = (n_videos + 255) / 256;
+    if (gx > 0x7fffffff) {
+        set_error("video_reduce: too many videos");
+        return VPDQ_B200_ERR_INVALID;
+    }
+    dim3 grid((unsigned)gx, (unsigned)(n_qvideos < 65535 ? n_qvideos : 65535));
+    k_video_reduce<<<grid, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(d_qmask), n_videos, d_qv_chunks,
+                                             d_qv_frames, n_qvideos, max_distance, d_matched_dense,
+                                             reinterpret_cast<int4*>(d_rows), (long long)cap, d_count);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;

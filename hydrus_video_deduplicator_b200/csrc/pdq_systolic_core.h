@@ -272,8 +272,8 @@ struct LaneState {
     }
 };
 // where the history value written at step u (u & 7 = U8) lives
-constexpr int hist_set(int U8) { return kBody == 8 ? ((((U8 + 8) & 7) >> 2) & 1) ^ 1 : 0; }
-constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
+VPDQS_HD constexpr int hist_set(int U8) { return kBody == 8 ? ((((U8 + 8) & 7) >> 2) & 1) ^ 1 : 0; }
+VPDQS_HD constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
 
 // M = 2^23 + byte: the byte at offset b of the little-endian word array spliced into the mantissa of 2^23 (PRMT)
 template <int N>

@@ -25,19 +25,13 @@ def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     return t.contiguous()
 
 
-_scratch: dict[tuple[int, int], torch.Tensor] = {}
-
-
 def pdq_scratch(n_frames: int, device: torch.device) -> torch.Tensor:
-    """Cached scratch for the PDQ passes (sized by the library; reused across calls on one stream)."""
+    """Scratch for one hash_frames call: the decimated 64x64 fp32 plane, 16 KB per frame.  Allocated per call through
+    torch's stream-ordered caching allocator (no cudaMalloc in steady state), so that calls on different streams or
+    threads never share a buffer and a buffer is not reused before the kernels that read it have run."""
     need = C.c_size_t(0)
     _ffi.check(_ffi.lib().vpdq_b200_pdq_scratch_bytes(int(n_frames), C.byref(need)))
-    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < need.value:
-        buf = torch.empty(need.value, dtype=torch.uint8, device=device)
-        _scratch[key] = buf
-    return buf
+    return torch.empty(need.value, dtype=torch.uint8, device=device)
 
 
 def hash_frames(frames: torch.Tensor, *, stages: bool = False):
@@ -133,6 +127,74 @@ def hamming_scan(db: torch.Tensor, query: torch.Tensor, offsets: torch.Tensor | 
             db.data_ptr(), n_db, offsets.data_ptr() if offsets is not None else None, n_videos, query.data_ptr(),
             n_q, int(tolerance), qmask.data_ptr(), tcount.data_ptr() if reverse_counts else None, _stream_ptr()))
     return (qmask, tcount) if reverse_counts else qmask
+
+
+def chunk_rows(q_offsets):
+    """Cut query videos (CSR q_offsets, host int array) into scan chunks of <= 64 frames.
+    -> (chunk_rows int32 [n_chunks + 1], qv_chunks int32 [n_qvideos + 1]): chunk c = query rows chunk_rows[c] ..
+    chunk_rows[c+1]-1; video q owns chunks qv_chunks[q] .. qv_chunks[q+1]-1 (an empty video owns none)."""
+    import numpy as np
+
+    q_offsets = np.asarray(q_offsets, dtype=np.int64)
+    n = np.diff(q_offsets)
+    per_video = (n + 63) // 64
+    qv_chunks = np.zeros(len(n) + 1, dtype=np.int64)
+    np.cumsum(per_video, out=qv_chunks[1:])
+    video_of_chunk = np.repeat(np.arange(len(n)), per_video)
+    k = np.arange(int(qv_chunks[-1])) - qv_chunks[video_of_chunk]           # chunk index inside its video
+    starts = q_offsets[video_of_chunk] + 64 * k
+    rows = np.empty(len(starts) + 1, dtype=np.int64)
+    rows[:-1] = starts
+    rows[-1] = q_offsets[-1]
+    return rows.astype(np.int32), qv_chunks.astype(np.int32)
+
+
+def video_matches(db: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, q_offsets, tolerance: int = 31, *,
+                  max_distance: int = 0, dense: bool = False, capacity: int | None = None):
+    """Score MANY query videos against every video of a database in one scan launch + one reduce launch:
+    matchHash / calculate_distance (vpdqpy.py:56, db/vptree.py:22-31) for all (query video, target video) pairs.
+      db [n, 32] uint8 CUDA + offsets [V + 1] int64 CUDA (CSR); queries [m, 32] uint8 CUDA + q_offsets (host ints, CSR,
+      videos contiguous from row 0)
+    -> rows [k, 4] int32 CUDA (query video, target video, matched query frames, distance) for the pairs with a match
+       (and distance <= max_distance if > 0), unordered; with dense=True instead matched [n_qvideos, V] int32."""
+    import numpy as np
+
+    db = _as_hash_matrix(db, "db")
+    queries = _as_hash_matrix(queries, "queries")
+    offsets = _need_cuda(offsets, "offsets", torch.int64)
+    dev = db.device
+    n_videos = offsets.numel() - 1
+    rows_h, qv_chunks_h = chunk_rows(q_offsets)
+    n_chunks, n_qv = len(rows_h) - 1, len(qv_chunks_h) - 1
+    frames_h = np.diff(np.asarray(q_offsets, dtype=np.int64)).astype(np.int32)
+    if n_videos == 0 or n_qv == 0 or n_chunks == 0 or db.shape[0] == 0:
+        if dense:
+            return torch.zeros((n_qv, n_videos), dtype=torch.int32, device=dev)
+        return torch.zeros((0, 4), dtype=torch.int32, device=dev)
+    meta = torch.from_numpy(np.concatenate([rows_h, qv_chunks_h, frames_h])).to(dev)
+    d_rows, d_qv_chunks, d_frames = meta[: n_chunks + 1], meta[n_chunks + 1: n_chunks + 2 + n_qv], meta[n_chunks + 2 + n_qv:]
+    qmask = torch.zeros((n_chunks, n_videos), dtype=torch.int64, device=dev)
+    L = _ffi.lib()
+    with torch.cuda.device(dev):
+        _ffi.check(L.vpdq_b200_hamming_scan_multi_dev(db.data_ptr(), db.shape[0], offsets.data_ptr(), n_videos,
+                                                      queries.data_ptr(), d_rows.data_ptr(), n_chunks, int(tolerance),
+                                                      qmask.data_ptr(), _stream_ptr()))
+        if dense:
+            matched = torch.empty((n_qv, n_videos), dtype=torch.int32, device=dev)
+            _ffi.check(L.vpdq_b200_video_match_dev(qmask.data_ptr(), n_videos, d_qv_chunks.data_ptr(), d_frames.data_ptr(),
+                                                   n_qv, 0, matched.data_ptr(), None, 0, None, _stream_ptr()))
+            return matched
+        cap = int(capacity) if capacity is not None else max(1024, 4 * n_qv)
+        while True:
+            out = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+            count = torch.zeros((1,), dtype=torch.int64, device=dev)
+            _ffi.check(L.vpdq_b200_video_match_dev(qmask.data_ptr(), n_videos, d_qv_chunks.data_ptr(), d_frames.data_ptr(),
+                                                   n_qv, int(max_distance), None, out.data_ptr(), cap, count.data_ptr(),
+                                                   _stream_ptr()))
+            n = int(count.item())
+            if n <= cap:
+                return out[:n]
+            cap = n  # the list overflowed: rerun the (cheap) reduce with room for everything
 
 
 def hamming_pairs(q: torch.Tensor, t: torch.Tensor, tolerance: int = 31, *, skip_diagonal: bool = False,

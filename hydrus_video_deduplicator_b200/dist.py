@@ -190,16 +190,16 @@ class ShardedIndex:
         self.d_off = torch.from_numpy(off).to(self.device)
 
     def matched_frames(self, query: np.ndarray | torch.Tensor, tolerance: int = 31) -> torch.Tensor:
-        """[n_videos] int32 on every rank: # query frames with a match in each video (chunks of 64)."""
+        """[n_videos] int32 on every rank: # query frames with a match in each video (any number of query frames:
+        one scan launch over the 64-frame chunks + the popcounts on the device, then the all_gather)."""
         from . import device as dev_api
 
         q = torch.as_tensor(query).reshape(-1, 32).to(self.device)
         n_local = self.d_off.numel() - 1
-        total = torch.zeros((n_local,), dtype=torch.int32, device=self.device)
-        if n_local and self.d_db.shape[0]:
-            for q0 in range(0, q.shape[0], 64):
-                mask = dev_api.hamming_scan(self.d_db, q[q0:q0 + 64], self.d_off, tolerance)
-                total += popcount64(mask)
+        if n_local and self.d_db.shape[0] and q.shape[0]:
+            total = dev_api.video_matches(self.d_db, self.d_off, q, [0, q.shape[0]], tolerance, dense=True)[0]
+        else:
+            total = torch.zeros((n_local,), dtype=torch.int32, device=self.device)
         return merge_video_masks(total)
 
     def candidate_pairs(self, queries: torch.Tensor, tolerance: int = 31, capacity: int = 1 << 20):
@@ -211,19 +211,3 @@ class ShardedIndex:
         if n > capacity:
             raise OverflowError(f"{n} pairs on rank {self.rank} exceed capacity {capacity}")
         return merge_pairs(pairs, self.first_frame), or_reduce(all_gather_bitmaps(bitmap))
-
-
-def popcount64(x: torch.Tensor) -> torch.Tensor:
-    """per-element popcount of an int64 tensor (SWAR; tiny vectors only -- plumbing, not the hot path)"""
-    x = x.clone()
-    m1, m2, m4 = 0x5555555555555555, 0x3333333333333333, 0x0F0F0F0F0F0F0F0F
-    lo = x & 0xFFFFFFFF
-    hi = (x >> 32) & 0xFFFFFFFF
-    out = torch.zeros_like(x, dtype=torch.int32)
-    for w in (lo, hi):
-        w = w - ((w >> 1) & (m1 & 0xFFFFFFFF))
-        w = (w & (m2 & 0xFFFFFFFF)) + ((w >> 2) & (m2 & 0xFFFFFFFF))
-        w = (w + (w >> 4)) & (m4 & 0xFFFFFFFF)
-        w = (w * 0x01010101) & 0xFFFFFFFF
-        out += (w >> 24).to(torch.int32)
-    return out

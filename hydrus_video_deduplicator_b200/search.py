@@ -101,6 +101,24 @@ class HashIndex:
         sim[np.diff(self.offsets) == 0] = 0.0  # empty stored hash: similar to nothing
         return sim
 
+    def within_radius(self, phash: bytes, max_distance: int, distance_tolerance: int = 31) -> list[tuple[int, int]]:
+        """[(row, distance)] of the stored videos with calculate_distance(phash, video) <= max_distance (<= 100), by
+        ascending row.  The scan over all 64-frame chunks of the query, the video-level reduce and the radius filter run
+        on the device; only the hits come back."""
+        phash = bytes(phash)
+        if len(phash) % _ffi.HASH_BYTES:
+            raise ValueError("phash must be a multiple of 32 bytes")
+        n_q = len(phash) // _ffi.HASH_BYTES
+        if n_q == 0 or len(self) == 0:
+            return []
+        rows = np.zeros((len(self), 4), dtype=np.int32)
+        n = C.c_int64(0)
+        _ffi.check(_ffi.lib().vpdq_b200_db_search_radius(self._db, phash, n_q, int(distance_tolerance), int(max_distance),
+                                                         rows.ctypes.data_as(C.c_void_p), len(self), C.byref(n)))
+        rows = rows[: n.value]
+        order = np.argsort(rows[:, 1], kind="stable")
+        return [(int(r[1]), int(r[3])) for r in rows[order]]
+
     def distances(self, phash: bytes) -> np.ndarray:
         """[n_videos] int64 == calculate_distance(phash, stored_video) (vptree.py:29-31)."""
         return (100 - self.similarities(phash).astype(np.int64)) + 1
@@ -117,9 +135,13 @@ class HashIndex:
                     if stored == phash:
                         best[hid] = 0
                 continue
-            d = self.distances(phash)
-            for row in np.nonzero(d <= max_hamming_distance)[0]:
-                hid, dist = self.hash_ids[int(row)], int(d[row])
+            if max_hamming_distance >= 101:  # even a video without a single matching frame (distance 101) is inside
+                d = self.distances(phash)
+                hits = [(int(row), int(d[row])) for row in np.nonzero(d <= max_hamming_distance)[0]]
+            else:
+                hits = self.within_radius(phash, max_hamming_distance)
+            for row, dist in hits:
+                hid = self.hash_ids[row]
                 if hid not in best or dist < best[hid]:
                     best[hid] = dist
         return dedupe_list(best.items())

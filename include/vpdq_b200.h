@@ -61,12 +61,6 @@ VPDQ_B200_API int vpdq_b200_device_count(int* count);
 VPDQ_B200_API int vpdq_b200_debug_flags(int device, int* flags);
 /* test hook: set (value != 0) or clear the flags above, to exercise the failure path */
 VPDQ_B200_API int vpdq_b200_debug_force_timeout(int device, int value);
-/* Which CUDA pipeline hashes RGB24 frames (all bit-identical; for A/B measurements and cross-checks):
- * 2 = frame-pair fused kernel kx_fused_jarosz2 (default), 1 = one-frame fused kernel kx_fused_jarosz,
- * 0 = v1 line kernels.  Initial value from the environment variable VPDQ_B200_PDQ_IMPL (fused | lines).
- * set returns VPDQ_B200_ERR_INVALID for any other value; get returns the current one. */
-VPDQ_B200_API int vpdq_b200_set_pdq_impl(int impl);
-VPDQ_B200_API int vpdq_b200_get_pdq_impl(void);
 /* number of CUDA kernels this library has launched in this process (monotonic) */
 VPDQ_B200_API int vpdq_b200_kernel_launches(uint64_t* count);
 /* the 16 x 64 fp32 DCT table the kernels use (host copy; bit-identical to the oracle's) */
@@ -94,7 +88,7 @@ VPDQ_B200_API int vpdq_b200_pdq_stages_dev(const uint8_t* d_frames, int channels
 
 /* First half of the frame hash on its own: RGB24 frames -> the Jarosz-filtered, decimated 64x64 luma plane
  * d_a64 [n][64][64] f32 (PDQ's "buffer64x64", the input of the quality metric and the DCT).  This is exactly the
- * fused kernel kx_fused_jarosz; bench.py times it alone for the roofline of the dominant kernel. */
+ * kernel kx_systolic_jarosz; bench.py times it alone for the roofline of the dominant kernel. */
 VPDQ_B200_API int vpdq_b200_pdq_jarosz_dev(const uint8_t* d_frames, int64_t n_frames, int width, int height,
                                            float* d_a64, void* stream);
 
@@ -160,6 +154,26 @@ VPDQ_B200_API int vpdq_b200_hamming_scan_dev(const uint64_t* d_db, int64_t n_db,
                                const uint64_t* d_query, int n_query, int tolerance, uint64_t* d_qmask,
                                int32_t* d_tcount, void* stream);
 
+/* The same scan for MANY query chunks in one launch (several query videos, or the 64-frame pieces of a long one):
+ *   d_query      [n_rows][4] u64      all query hashes, 32-byte aligned
+ *   d_chunk_rows [n_chunks + 1] i32   chunk c = query rows d_chunk_rows[c] .. d_chunk_rows[c+1]-1 (at most 64)
+ *   d_qmask      [n_chunks][n_videos] u64  OUT  as above, one row of masks per chunk; ORs, zero it first */
+VPDQ_B200_API int vpdq_b200_hamming_scan_multi_dev(const uint64_t* d_db, int64_t n_db, const int64_t* d_offsets,
+                                     int64_t n_videos, const uint64_t* d_query, const int32_t* d_chunk_rows, int n_chunks,
+                                     int tolerance, uint64_t* d_qmask, void* stream);
+
+/* Video-level reduce of scan masks == vpdq.matchHash + calculate_distance for every (query video, target video)
+ * (vpdqpy.py:56, db/vptree.py:22-31), on the device:
+ *   query video q owns chunks d_qv_chunks[q] .. d_qv_chunks[q+1]-1 of d_qmask and has d_qv_frames[q] frames;
+ *   matched(q, v) = # query frames of q with >= 1 match in target video v; distance = (100 - 100*matched/n_q) + 1.
+ *   d_matched [n_qvideos][n_videos] i32  OUT (optional) matched(q, v), dense
+ *   d_rows    [cap][4] i32               OUT (optional, 16-byte aligned) one row (q, v, matched, distance) per pair
+ *                                        with matched > 0 and (max_distance <= 0 or distance <= max_distance), unordered
+ *   d_count   [1] u64                    OUT number of rows (may exceed cap; adds) */
+VPDQ_B200_API int vpdq_b200_video_match_dev(const uint64_t* d_qmask, int64_t n_videos, const int32_t* d_qv_chunks,
+                              const int32_t* d_qv_frames, int n_qvideos, int max_distance, int32_t* d_matched,
+                              int32_t* d_rows, int64_t cap, unsigned long long* d_count, void* stream);
+
 /* Brute-force all pairs between two hash sets (self-join when both are the same buffer).
  *   d_any   [(n_q + 31) / 32] u32  OUT (optional) bit i: query i has >= 1 match ("candidate bitmap"); ORs
  *   d_pairs [cap] u64              OUT (optional) (i << 32) | j for every match, unordered
@@ -185,6 +199,12 @@ VPDQ_B200_API int vpdq_b200_db_create(int device, const uint8_t* h_db, int64_t n
                         vpdq_b200_db** out);
 VPDQ_B200_API int vpdq_b200_db_search(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_query, int tolerance,
                         int32_t* h_matched /* [n_videos] */);
+/* The same search, answered compactly: rows (0, video, matched, distance) for the stored videos with matched > 0 and
+ * distance <= max_distance (= VpTreeManager.search_file's radius, vptree.py:865-902; <= 0: every video with a
+ * match).  *n_rows = number found (VPDQ_B200_ERR_OVERFLOW if larger than cap).  One upload, one scan launch over all
+ * 64-frame chunks of the query, the reduce on the device, one small read-back. */
+VPDQ_B200_API int vpdq_b200_db_search_radius(vpdq_b200_db* db, const uint8_t* h_query, int64_t n_query, int tolerance,
+                               int max_distance, int32_t* h_rows /* [cap][4] */, int64_t cap, int64_t* n_rows);
 VPDQ_B200_API int vpdq_b200_db_destroy(vpdq_b200_db* db);
 
 /* One-shot form of the above (creates, searches, destroys).  Any n_query (chunks of 64 inside). */

@@ -6,7 +6,7 @@
 // Build: g++ -O1 -ffp-contract=off -shared -fPIC -o libpdq_fused_emu.so pdq_fused_emu.cpp
 #include <stdlib.h>
 
-#include "../../hydrus_video_deduplicator_b200/csrc/pdq_fused_core.h"
+#include "../legacy/pdq_fused_core.h"
 
 using namespace vpdq_core;
 

@@ -19,7 +19,7 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "legacy.cuh"
 #include "pdq_fused_core.h"
 
 namespace vpdq {
@@ -173,17 +173,6 @@ int fused_debug_flags(int* flags) {
     *flags = v;
     return VPDQ_B200_OK;
 }
-
-int fused_timeout_flag_async(int* h_flag, cudaStream_t stream) {
-    VPDQ_CUDA(cudaMemcpyFromSymbolAsync(h_flag, g_fused_timeout, sizeof(int), 0, cudaMemcpyDeviceToHost, stream));
-    return VPDQ_B200_OK;
-}
-int fused_force_timeout(int value) {
-    VPDQ_CUDA(cudaMemcpyToSymbol(g_fused_timeout, &value, sizeof value));
-    return VPDQ_B200_OK;
-}
-
-size_t fused_scratch_per_frame() { return (size_t)64 * 64 * sizeof(float); }
 
 // tensor map over the whole batch seen as [n*512 rows][512*channels B], box = 32 rows x 112 B (RGB24) or 48 B (gray)
 // (shared with pdq_fused2.cu)

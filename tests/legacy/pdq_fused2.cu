@@ -17,13 +17,12 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "legacy.cuh"
 #include "pdq_fused2_core.h"
 
 namespace vpdq {
 using namespace vpdq_core2;
 
-int fused_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, int channels, CUtensorMap* tmap);  // pdq_fused.cu
 
 constexpr int kFused2Threads = 32 * kWarps;  // 288
 
@@ -207,15 +206,6 @@ int fused2_debug_flags(int* flags) {
     int v = 0;
     VPDQ_CUDA(cudaMemcpyFromSymbol(&v, g_fused2_timeout, sizeof v));
     *flags = v;
-    return VPDQ_B200_OK;
-}
-
-int fused2_timeout_flag_async(int* h_flag, cudaStream_t stream) {
-    VPDQ_CUDA(cudaMemcpyFromSymbolAsync(h_flag, g_fused2_timeout, sizeof(int), 0, cudaMemcpyDeviceToHost, stream));
-    return VPDQ_B200_OK;
-}
-int fused2_force_timeout(int value) {
-    VPDQ_CUDA(cudaMemcpyToSymbol(g_fused2_timeout, &value, sizeof value));
     return VPDQ_B200_OK;
 }
 

@@ -100,6 +100,19 @@ def test_cpulist_parsing():
     assert hdist.bind_to_gpu_numa_node(0) is None or isinstance(hdist.bind_to_gpu_numa_node(0), int)
 
 
-def test_popcount64():
-    x = torch.tensor([0, 1, -1, 0x00FF00FF00FF00FF, 1 << 62, -(1 << 63)], dtype=torch.int64)
-    assert hdist.popcount64(x).tolist() == [0, 1, 64, 32, 1, 1]
+def test_query_chunking():
+    """device.chunk_rows: query videos cut into scan chunks of <= 64 frames -- ragged, empty and exactly-64 videos."""
+    from hydrus_video_deduplicator_b200 import device
+
+    lens = [0, 1, 64, 65, 128, 0, 300, 63, 0]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    rows, qv = device.chunk_rows(off)
+    assert qv.tolist() == [0, 0, 1, 2, 4, 6, 6, 11, 12, 12]
+    assert rows[0] == 0 and rows[-1] == off[-1] and (np.diff(rows) <= 64).all() and (np.diff(rows) > 0).all()
+    for v, n in enumerate(lens):  # every video's chunks tile exactly its rows
+        c0, c1 = qv[v], qv[v + 1]
+        assert c1 - c0 == (n + 63) // 64
+        if n:
+            assert rows[c0] == off[v] and rows[c1] == off[v + 1]
+    rows, qv = device.chunk_rows([0])
+    assert rows.tolist() == [0] and qv.tolist() == [0]

@@ -1,7 +1,8 @@
-"""CPU check of the fused PDQ kernel's schedule (kx_fused_jarosz): the emulator in tests/emu compiles the very
-header the CUDA kernel is built from (csrc/pdq_fused_core.h) and executes it step by step; its output must
-equal the oracle's decimated 64x64 plane bit for bit -- for every grid size (frames per CTA 0, 1, many; CTA
-ranges starting mid-batch).  Also checks the branch-free exact division by 3 the kernel uses."""
+"""CPU check of the PDQ kernels' schedules: the emulators in tests/emu compile the very headers the CUDA kernels are
+built from (the product's csrc/pdq_systolic_core.h; the test-only tests/legacy/pdq_fused*_core.h of the round-1
+tiled kernels) and execute them step by step; the output must equal the oracle's decimated 64x64 plane bit for bit
+-- for every work split (frames per warp / CTA 0, 1, many; ranges starting mid-batch).  Also checks the branch-free
+exact division by 3 the kernels use."""
 from __future__ import annotations
 
 import ctypes as C

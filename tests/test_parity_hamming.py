@@ -201,3 +201,72 @@ def test_baseline_sizes_vs_oracle_slabs(torch_dev):
     refp = oracle.hamming_pairs(planted.cpu().numpy(), db_h[:m], 31)
     assert cnt == len(refp) == nq
     assert {tuple(p) for p in pairs.cpu().numpy().tolist()} == {tuple(p) for p in refp.tolist()}
+
+
+def test_video_matches_many_queries_vs_oracle(torch_dev):
+    """vpdq_b200_hamming_scan_multi_dev + vpdq_b200_video_match_dev: MANY query videos (ragged, empty, > 64 frames)
+    against a ragged database with empty videos, in one scan launch and one reduce launch: the dense matched counts
+    equal the oracle's for every (query video, target video), the compact rows equal the oracle's search_file lists
+    (matchHash numerator and calculate_distance, db/vptree.py:22-31)."""
+    torch, dev = torch_dev
+    from hydrus_video_deduplicator_b200 import device
+
+    vids, offsets = synth.synth_video_db(300, 0, seed=8, dup_frac=0.4)
+    rng = np.random.default_rng(3)
+    long_vid = np.concatenate([np.frombuffer(vids[k], np.uint8).reshape(-1, 32) for k in (5, 9, 40, 77, 120, 201, 250)] * 4)
+    vids[33] = long_vid.tobytes()  # a long video: several scan chunks
+    vids[34] = long_vid[:64].tobytes()  # exactly one full chunk
+    offsets = np.concatenate([[0], np.cumsum([len(v) // 32 for v in vids])]).astype(np.int64)
+    assert len(vids[33]) // 32 > 64 and (np.diff(offsets) == 0).any()
+    db = np.frombuffer(b"".join(vids), np.uint8).reshape(-1, 32)
+    d_db = torch.from_numpy(db.copy()).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    q_ids = [33, 34, 0, 1, 2, 3, 150, 299] + [int(v) for v in np.flatnonzero(np.diff(offsets) == 0)[:2]]
+    q = np.concatenate([np.frombuffer(vids[v], np.uint8).reshape(-1, 32) for v in q_ids])
+    q_off = np.concatenate([[0], np.cumsum([len(vids[v]) // 32 for v in q_ids])])
+    d_q = torch.from_numpy(q.copy()).to(dev)
+    dense = device.video_matches(d_db, d_off, d_q, q_off, 31, dense=True).cpu().numpy()
+    for k, v in enumerate(q_ids):
+        qv = np.frombuffer(vids[v], np.uint8).reshape(-1, 32)
+        want = oracle.video_matched(qv, db, offsets, 31) if len(qv) else np.zeros(len(vids), np.int32)
+        assert (dense[k] == want).all(), v
+    for radius in (26, 51, 0):
+        rows = device.video_matches(d_db, d_off, d_q, q_off, 31, max_distance=radius).cpu().numpy()
+        got = {}
+        for qi, tv, m, d in rows.tolist():
+            got.setdefault(qi, set()).add((tv, d))
+            assert m == dense[qi, tv]
+        for k, v in enumerate(q_ids):
+            want = set(oracle.search_file(vids, v, radius if radius else 101))
+            if radius == 0:  # no distance filter: every video with at least one matching frame
+                want = {(tv, d) for tv, d in want if dense[k, tv] > 0}
+            assert got.get(k, set()) == {(tv, d) for tv, d in want if dense[k, tv] > 0}, (v, radius)
+
+
+def test_db_search_long_queries_and_radius():
+    """vpdq_b200_db_search / _search_radius: any number of query frames in one launch sequence (the popcounts on the
+    device, one synchronisation) -- checked for 1, 64, 65 and 300+ query frames against the oracle."""
+    import ctypes as C
+
+    from hydrus_video_deduplicator_b200 import _ffi
+
+    vids, offsets = synth.synth_video_db(500, 0, seed=21, dup_frac=0.3)
+    db = np.frombuffer(b"".join(vids), np.uint8).reshape(-1, 32)
+    index = search.HashIndex(list(range(100, 600)), vids)
+    rng = np.random.default_rng(5)
+    for n_q in (1, 64, 65, 333):
+        rows = rng.integers(0, len(db), size=n_q)
+        q = np.ascontiguousarray(db[rows])
+        q[::3] = np.stack([synth.flip_bits(h, 30, rng) for h in q[::3]])
+        got = index.matched_frames(q.tobytes())
+        want = oracle.video_matched(q, db, offsets, 31)
+        assert (got == want).all(), n_q
+        for radius in (26, 51):
+            out = np.zeros((len(vids), 4), np.int32)
+            n = C.c_int64(0)
+            _ffi.check(_ffi.lib().vpdq_b200_db_search_radius(index._db, q.tobytes(), n_q, 31, radius,
+                                                             out.ctypes.data_as(C.c_void_p), len(vids), C.byref(n)))
+            dist = (100 - (100 * want.astype(np.int64)) // n_q) + 1
+            ref = {(int(v), int(want[v]), int(dist[v])) for v in np.flatnonzero((want > 0) & (dist <= radius))}
+            assert {(r[1], r[2], r[3]) for r in out[: n.value].tolist()} == ref, (n_q, radius)
+    index.close()
