@@ -80,7 +80,9 @@ struct CudaDev {
     };
     int device = 0, channels = 3;
     size_t frame_bytes = 0, n_slots = 0;
-    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    static constexpr int kComputeStreams = 3;  // consecutive launches run concurrently (small ones leave most SMs idle)
+    cudaStream_t copy_stream = nullptr, compute_streams[kComputeStreams] = {};
+    unsigned next_stream = 0;
     cudaEvent_t uploaded = nullptr;
     uint8_t *h_frames = nullptr, *d_frames = nullptr, *h_hash = nullptr, *d_hash = nullptr;
     int32_t *h_quality = nullptr, *d_quality = nullptr;
@@ -95,7 +97,7 @@ struct CudaDev {
         frame_bytes = fb;
         VPDQ_CUDA(cudaSetDevice(device));
         VPDQ_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        VPDQ_CUDA(cudaStreamCreateWithFlags(&compute_stream, cudaStreamNonBlocking));
+        for (auto& st : compute_streams) VPDQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         VPDQ_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
         VPDQ_CUDA(cudaHostAlloc(&h_frames, n * fb, cudaHostAllocDefault));
         VPDQ_CUDA(cudaMalloc(&d_frames, n * fb));
@@ -105,7 +107,7 @@ struct CudaDev {
         memset(h_flags, 0, 4 * sizeof(int));
         VPDQ_CUDA(cudaMalloc(&d_hash, n * 32));
         VPDQ_CUDA(cudaMalloc(&d_quality, n * sizeof(int32_t)));
-        scratch_bytes = pdq_scratch_bytes((int64_t)n);
+        scratch_bytes = pdq_scratch_bytes((int64_t)n);  // one plane per SLOT: concurrent launches use disjoint parts
         VPDQ_CUDA(cudaMalloc(&d_scratch, scratch_bytes));
         *hf = h_frames;
         *df = d_frames;
@@ -119,10 +121,13 @@ struct CudaDev {
         return VPDQ_B200_OK;
     }
     int launch(size_t first_slot, size_t n, Event* out) {
+        cudaStream_t compute_stream = compute_streams[next_stream++ % kComputeStreams];
         VPDQ_CUDA(cudaEventRecord(uploaded, copy_stream));
         VPDQ_CUDA(cudaStreamWaitEvent(compute_stream, uploaded, 0));
         int rc = pdq_launch(d_frames + first_slot * frame_bytes, channels, (int64_t)n, d_hash + first_slot * 32,
-                            d_quality + first_slot, nullptr, nullptr, d_scratch, scratch_bytes, compute_stream);
+                            d_quality + first_slot, nullptr, nullptr,
+                            static_cast<uint8_t*>(d_scratch) + first_slot * pdq_scratch_per_frame(),
+                            n * pdq_scratch_per_frame(), compute_stream);
         if (rc) return rc;
         VPDQ_CUDA(cudaMemcpyAsync(h_hash + first_slot * 32, d_hash + first_slot * 32, n * 32, cudaMemcpyDeviceToHost,
                                   compute_stream));
@@ -199,7 +204,9 @@ int get_service(int device, int channels, Service** out) {
         cfg.copy_workers = env_int("VPDQ_B200_COPY_THREADS", (int)(cores >= 16 ? 8 : cores >= 4 ? cores / 2 : 2), 1, 64);
         cfg.copy_parts = 4;
         cfg.max_launch = cfg.arena_frames;
-        cfg.max_inflight = 2;
+        cfg.max_inflight = CudaDev::kComputeStreams;
+        cfg.launch_min = env_int("VPDQ_B200_LAUNCH_MIN", 64, 1, cfg.arena_frames);
+        cfg.spin_us = env_int("VPDQ_B200_SPIN_US", 2000, 0, 1000000);
         slot.dev = new CudaDev;
         slot.dev->device = device;
         slot.dev->channels = channels;
@@ -521,7 +528,7 @@ int vpdq_b200_hasher_finish(vpdq_b200_hasher* h, int quality_keep, uint8_t* h_ha
         return VPDQ_B200_ERR_INVALID;
     }
     const int err = h->svc->wait_all(&h->st);  // this hasher's frames only
-    std::lock_guard<std::mutex> lk(h->st.mu);
+    std::unique_lock<std::mutex> lk(h->st.mu);
     const int64_t n = h->st.pushed;
     int64_t kept = 0;
     if (!err) {
@@ -536,12 +543,13 @@ int vpdq_b200_hasher_finish(vpdq_b200_hasher* h, int quality_keep, uint8_t* h_ha
     *n_kept = kept;
     // reset: a healthy hasher is reusable (nothing of it is in flight any more); after an error the results are
     // dropped and the error stays (the service of this device is broken for good: fail loudly, never guess)
-    h->st.hashes.clear();
-    h->st.quality.clear();
+    lk.unlock();
     if (!err) {
-        h->st.pushed = 0;
-        h->st.done = 0;
-        h->st.consumed.store(0, std::memory_order_release);
+        h->st.reset();
+    } else {
+        std::lock_guard<std::mutex> lk2(h->st.mu);
+        h->st.hashes.clear();
+        h->st.quality.clear();
     }
     if (err) {
         set_error("hasher_finish: the hashing service of device %d failed (%d; a CUDA error or a TMA copy that never "

@@ -40,8 +40,16 @@ struct Config {
     int copy_workers = 4;
     int copy_parts = 4;       // a frame is copied in this many parts (latency of the last frame of a short video)
     int max_launch = 2048;    // frames per kernel launch
-    int max_inflight = 2;     // launches in flight
+    int max_inflight = 3;     // launches in flight
+    int launch_min = 64;      // launch as soon as this many uploaded frames are waiting; fewer only when a finish() is
+                              // waiting for them (a launch has a fixed latency of ~0.2 ms: launching frame by frame as
+                              // they trickle in would serialise a short video into several of those)
+    int spin_us = 2000;       // how long idle threads poll before they sleep (a hashing session pushes continuously)
 };
+
+// memcpy into the pinned ring with non-temporal stores: the destination is read next by the DMA engine, not by a CPU,
+// so write-allocating it in the cache only costs memory bandwidth (one third of the copy's traffic)
+inline void copy_to_pinned(uint8_t* dst, const uint8_t* src, size_t n);
 
 struct HasherState {
     std::mutex mu;
@@ -50,10 +58,51 @@ struct HasherState {
     std::vector<int32_t> quality;    // [pushed]
     int64_t pushed = 0;              // guarded by mu
     int64_t done = 0;                // guarded by mu
+    std::atomic<int64_t> done_pub{0};   // = done, readable without the lock (finish() polls it before it sleeps)
+    std::atomic<int64_t> pushed_pub{0};
+    int64_t last_slot = -1;          // ring counter of the most recently pushed frame (guarded by the service mutex)
     std::atomic<int64_t> consumed{0};  // frames whose source bytes have been copied out (contiguous watermark)
     int error = 0;                   // first device error that hit one of this hasher's frames
     int waiters = 0;
+    // after wait_all() returned without error nothing of this hasher is in flight: make it reusable
+    void reset() {
+        std::lock_guard<std::mutex> lk(mu);
+        hashes.clear();
+        quality.clear();
+        pushed = done = 0;
+        pushed_pub.store(0, std::memory_order_release);
+        done_pub.store(0, std::memory_order_release);
+        consumed.store(0, std::memory_order_release);
+    }
 };
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) inline void copy_nt_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+inline void copy_to_pinned(uint8_t* dst, const uint8_t* src, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && n >= 4096 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0)
+        copy_nt_avx2(dst, src, n);
+    else
+        memcpy(dst, src, n);
+}
+#else
+inline void copy_to_pinned(uint8_t* dst, const uint8_t* src, size_t n) { memcpy(dst, src, n); }
+#endif
 
 template <class Dev>
 class HashService {
@@ -115,9 +164,11 @@ class HashService {
                 {
                     std::lock_guard<std::mutex> hk(h->mu);
                     s.seq = h->pushed++;
+                    h->pushed_pub.store(h->pushed, std::memory_order_release);
                     h->hashes.resize((size_t)h->pushed * 32);
                     h->quality.resize((size_t)h->pushed);
                 }
+                h->last_slot = c;
                 s.parts_left.store(cfg_.copy_parts, std::memory_order_relaxed);
                 s.waiter = wait_copied ? &my_parts : nullptr;
                 if (wait_copied) my_parts.fetch_add(cfg_.copy_parts, std::memory_order_relaxed);
@@ -151,6 +202,20 @@ class HashService {
 
     // block until every frame pushed to h has its result (or an error)
     int wait_all(HasherState* h) {
+        {   // ask the pump to launch everything up to this hasher's last frame now, however few frames that is
+            std::lock_guard<std::mutex> lk(mu_);
+            const int64_t upto = h->last_slot + 1;
+            int64_t cur = flush_upto_.load(std::memory_order_relaxed);
+            while (cur < upto && !flush_upto_.compare_exchange_weak(cur, upto, std::memory_order_release)) {
+            }
+            if (pump_sleeping_) cv_pump_.notify_one();
+        }
+        // results usually arrive within a fraction of a millisecond: poll before paying for a futex sleep + wake-up
+        const auto t0 = std::chrono::steady_clock::now();
+        while (h->done_pub.load(std::memory_order_acquire) < h->pushed_pub.load(std::memory_order_acquire)) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(cfg_.spin_us)) break;
+            std::this_thread::yield();
+        }
         std::unique_lock<std::mutex> lk(h->mu);
         ++h->waiters;
         while (h->done < h->pushed && h->error == 0) h->cv.wait(lk);
@@ -189,7 +254,7 @@ class HashService {
             t = tasks_.front();
             tasks_.pop_front();
         }
-        memcpy(t.dst, t.src, t.bytes);
+        copy_to_pinned(t.dst, t.src, t.bytes);
         Slot& s = slots_[t.slot];
         std::atomic<int64_t>* waiter = s.waiter;  // read before the release below: the slot may be recycled afterwards
         s.parts_left.fetch_sub(1, std::memory_order_acq_rel);
@@ -203,7 +268,7 @@ class HashService {
             // spin briefly (the next frame of a video usually follows within microseconds), then sleep
             bool got = false;
             const auto t0 = std::chrono::steady_clock::now();
-            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(100)) {
+            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(cfg_.spin_us)) {
                 if (run_one_task()) {
                     got = true;
                     break;
@@ -255,6 +320,7 @@ class HashService {
                     o->quality[(size_t)s.seq] = h_quality_[k % A];
                 }
                 o->done += e - c;
+                o->done_pub.store(o->done, std::memory_order_release);
                 if (rc && !o->error) o->error = rc;
                 if (o->waiters) o->cv.notify_all();
             }
@@ -273,6 +339,7 @@ class HashService {
         const size_t fb = cfg_.frame_bytes;
         int64_t uploaded = 0, launched = 0;
         std::deque<Launch> inflight;
+        auto idle_since = std::chrono::steady_clock::now();
         for (;;) {
             bool progressed = false;
             // (1) retire finished launches, oldest first
@@ -307,8 +374,12 @@ class HashService {
                 uploaded = u;
                 progressed = true;
             }
-            // (3) launch over everything uploaded, at most max_inflight launches in flight
-            if (launched < uploaded && (int)inflight.size() < cfg_.max_inflight) {
+            // (3) launch over what is uploaded: when enough frames wait, or a finish() waits for some of them, or pushes
+            // are blocked on a full ring; at most max_inflight launches in flight
+            const int64_t waiting = uploaded - launched;
+            const bool flush = flush_upto_.load(std::memory_order_acquire) > launched;
+            if (waiting > 0 && (int)inflight.size() < cfg_.max_inflight &&
+                (waiting >= cfg_.launch_min || flush || head_pub_.load(std::memory_order_acquire) - tail_.load() >= A)) {
                 int64_t e = launched - (launched % A) + A;
                 if (e > uploaded) e = uploaded;
                 if (e - launched > cfg_.max_launch) e = launched + cfg_.max_launch;
@@ -323,16 +394,27 @@ class HashService {
                 launched = e;
                 progressed = true;
             }
-            if (progressed) continue;
-            {
+            if (progressed) {
+                idle_since = std::chrono::steady_clock::now();
+                continue;
+            }
+            const bool outstanding = !inflight.empty() || head_pub_.load(std::memory_order_acquire) != uploaded;
+            if (!outstanding && std::chrono::steady_clock::now() - idle_since > std::chrono::microseconds(cfg_.spin_us)) {
                 std::unique_lock<std::mutex> lk(mu_);
-                if (stop_ && inflight.empty()) return;
-                if (inflight.empty() && head_ == uploaded) {  // nothing outstanding anywhere: sleep until a push
+                if (stop_) return;
+                // nothing outstanding anywhere for a while: sleep until a push or a finish() (uploaded frames that no
+                // finish() has asked for yet can wait with us)
+                if (head_ == uploaded && flush_upto_.load(std::memory_order_acquire) <= launched) {
                     pump_sleeping_ = true;
                     cv_pump_.wait(lk);
                     pump_sleeping_ = false;
-                    continue;
+                    idle_since = std::chrono::steady_clock::now();
                 }
+                continue;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (stop_ && inflight.empty()) return;
             }
             dev_->idle_pause(!inflight.empty());
         }
@@ -351,6 +433,7 @@ class HashService {
     int64_t head_ = 0;
     std::atomic<int64_t> head_pub_{0};
     std::atomic<int64_t> tail_{0};
+    std::atomic<int64_t> flush_upto_{0};  // frames below this ring counter are wanted by a finish(): launch them now
     int space_waiters_ = 0;
     bool pump_sleeping_ = false;
     bool stop_ = true;

@@ -37,3 +37,26 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir() -> Path:
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="session")
+def bbb_clip_frames(golden_dir):
+    """{clip file name: (frame indices [k], frames [k, 512, 512, 3] uint8, golden hashes [10, 32] uint8)} for the five
+    OpenCV-decodable Big Buck Bunny clips (tests/golden/make_golden.py): post-POINT-resize frames, PNG-compressed."""
+    import cv2
+    import numpy as np
+
+    z = np.load(golden_dir / "bbb_clip_frames.npz")
+    out = {}
+    for p in sorted((golden_dir / "video_hashes").glob("S01_Big_Buck_Bunny*.txt")):
+        name = p.name[:-4]
+        key = name.replace(".", "_").replace("-", "_")
+        if key + "__idx" not in z:
+            continue
+        idx = z[key + "__idx"]
+        frames = np.stack([cv2.cvtColor(cv2.imdecode(z[f"{key}__png{j}"], cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+                           for j in range(len(idx))])
+        gold = np.frombuffer(bytes.fromhex(p.read_text().strip()), np.uint8).reshape(-1, 32)
+        out[name] = (idx, np.ascontiguousarray(frames), gold)
+    assert len(out) == 5
+    return out

@@ -101,7 +101,7 @@ extern "C" __attribute__((visibility("default"))) int emu_service_run(int arena_
                     if (svc.push(h, buf.data() + (size_t)k * frame_bytes, 1, (k & 1) != 0)) ++errors;
                 if (k < n && svc.push(h, buf.data() + (size_t)k * frame_bytes, n - k, (v & 1) != 0)) ++errors;
                 if (svc.wait_all(h)) ++errors;
-                std::lock_guard<std::mutex> lk(h->mu);
+                std::unique_lock<std::mutex> lk(h->mu);
                 if (h->pushed != n || h->done != n) ++errors;
                 if (h->consumed.load() != n) ++errors;  // every source byte has been copied out when finish returns
                 for (int j = 0; j < n; ++j) {
@@ -110,10 +110,8 @@ extern "C" __attribute__((visibility("default"))) int emu_service_run(int arena_
                     memcpy(&got_seq, h->hashes.data() + (size_t)j * 32 + 8, 8);
                     if (got_id != id || got_seq != j || h->quality[j] != j % 101) ++errors;
                 }
-                h->hashes.clear();
-                h->quality.clear();
-                h->pushed = h->done = 0;
-                h->consumed.store(0);
+                lk.unlock();
+                h->reset();
             }
             delete h;
         });

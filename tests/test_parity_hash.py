@@ -38,6 +38,24 @@ def test_gif_known_answer_on_gpu(golden_dir, torch_dev):
     assert (quality == 100).all()
 
 
+def test_soft_pin_on_the_other_decodable_golden_clips_gpu(bbb_clip_frames):
+    """test_vpdqpy.py:116-128 through the drop-in surface on the GPU: frames of the five h264 / vp9 golden clips ->
+    VideoHasher -> `100 - matchHash(ours, golden) < 1.0`; bit-identical to the oracle, and one frame per clip equals
+    the reference's stored hash exactly."""
+    for name, (idx, frames, gold) in bbb_clip_frames.items():
+        hasher = vpdq.VideoHasher(1, 512, 512, 0)
+        for f in frames:
+            hasher.hash_frame(f.tobytes())
+        phash, all_h, all_q = hasher.finish(return_all=True)
+        hasher.close()
+        ref_h, ref_q = oracle.pdq_hash_frames(frames, nthreads=2)
+        assert all_h == ref_h.tobytes() and all_q == ref_q.tolist(), name
+        golden = vpdq.VpdqHash(gold.tobytes())
+        assert 100.0 - vpdq.matchHash(phash, golden, 31) < 1.0, name
+        got = np.frombuffer(all_h, np.uint8).reshape(-1, 32)
+        assert any(got[j].tobytes() == gold[k].tobytes() for j, k in enumerate(idx)), name
+
+
 def test_device_point_resize_and_native_hash(golden_dir, torch_dev):
     """8f-2: swscale POINT resize on the device == the host index rule, for several native sizes; and the golden
     GIF clip hashed from its NATIVE 360x640 frames entirely on the device reproduces the reference's hashes."""
