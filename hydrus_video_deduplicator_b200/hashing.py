@@ -12,6 +12,12 @@ def compute_phash(video: Path | str | bytes, num_threads: int = 0) -> VpdqHash:
     return Vpdq.computeHash(video, num_threads)
 
 
+def compute_phashes(videos, num_threads: int = 0) -> list[VpdqHash]:
+    """compute_phash for many videos at once: host decode pool -> shared GPU submission service (no reference
+    counterpart: the reference hashes file after file, dedup.py:346-352)."""
+    return Vpdq.computeHashes(videos, num_threads)
+
+
 def encode_phash_to_str(phash: VpdqHash) -> str:
     """hashing.py:24-31"""
     return str(phash)

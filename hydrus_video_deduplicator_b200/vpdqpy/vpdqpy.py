@@ -7,9 +7,11 @@ Same static methods, argument meaning and exceptions:
     Vpdq.is_similar        vpdqpy.py:122-131
 
 Decoding is NOT part of the accelerated path: frames are decoded on the host with PyAV
-when it is installed (exactly the reference's code path) and with OpenCV's bundled FFmpeg otherwise,
-sampled every round(fps)-th frame and POINT-resized to 512x512 RGB24 -- then every frame goes through
-VideoHasher.hash_frame -> CUDA.
+when it is installed (exactly the reference's code path) and with OpenCV's bundled FFmpeg otherwise (with a
+warning: that path is not bit-compatible), sampled every round(fps)-th frame and POINT-resized to 512x512
+RGB24 -- then every frame goes through VideoHasher.hash_frame -> CUDA.  Vpdq.computeHashes is the decode feed
+for many videos: a host decode pool whose hashers all feed the device's one submission service, which applies
+the back-pressure.
 """
 from __future__ import annotations
 
@@ -113,6 +115,7 @@ class Vpdq:
         with tempfile.NamedTemporaryFile(suffix=".video", delete=False) as tmp:
             tmp.write(video_bytes)
             path = tmp.name
+        cap = None
         try:
             cap = cv2.VideoCapture(path)
             if not cap.isOpened():
@@ -127,15 +130,27 @@ class Vpdq:
                 if frame_index % average_fps == 0:
                     yield point_resize_rgb(bgr[:, :, ::-1]).tobytes()
                 frame_index += 1
-            cap.release()
-        finally:
+        finally:  # also when the generator is abandoned early
+            if cap is not None:
+                cap.release()
             os.unlink(path)
+
+    _warned_cv2 = False
 
     @staticmethod
     def frame_extract(video_bytes: bytes) -> Iterator[bytes]:
         try:
             import av  # noqa: F401, PLC0415
         except ImportError:
+            if not Vpdq._warned_cv2:
+                Vpdq._warned_cv2 = True
+                import warnings
+
+                warnings.warn(
+                    "PyAV is not installed: decoding with OpenCV instead.  That path is NOT bit-compatible with the "
+                    "reference's (sampling on CAP_PROP_FPS instead of average_rate, rotation metadata applied, OpenCV's "
+                    "YUV->RGB conversion): hashes may differ from the reference's by a few bits per frame.",
+                    RuntimeWarning, stacklevel=2)
             return Vpdq.frame_extract_cv2(video_bytes)
         return Vpdq.frame_extract_pyav(video_bytes)
 
@@ -153,6 +168,24 @@ class Vpdq:
             return hasher.finish()
         finally:
             hasher.close()
+
+    @staticmethod
+    def computeHashes(video_files, num_threads: int = 0) -> list:
+        """Decode feed for MANY videos: a pool of host decode threads (FFmpeg releases the GIL), one
+        VideoHasher per video as in computeHash.  All hashers feed the device's one submission service, so frames of
+        different videos share uploads and kernel launches, and a full ring blocks the decoders -- the reference's
+        hash_frame back-pressure (vpdqpy.py:115-117) -- instead of buffering frames without bound.
+        num_threads <= 0: min(8, cpu count).  Returns the VpdqHash of every video, in input order; a video that
+        fails to decode raises from here exactly as computeHash would."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        videos = list(video_files)
+        n = num_threads if num_threads and num_threads > 0 else min(8, os.cpu_count() or 1)
+        if len(videos) <= 1 or n == 1:
+            return [Vpdq.computeHash(v) for v in videos]
+        with ThreadPoolExecutor(max_workers=n) as pool:
+            return list(pool.map(Vpdq.computeHash, videos))
 
     @staticmethod
     def is_similar(vpdq_features1: VpdqHash, vpdq_features2: VpdqHash, threshold: float = 75.0) -> tuple[bool, float]:

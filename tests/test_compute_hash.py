@@ -64,3 +64,18 @@ def test_compute_phash_matches_oracle(tmp_path):
     assert hashing.decode_phash_from_str(hashing.encode_phash_to_str(phash)) == phash
     similar, sim = Vpdq.is_similar(phash, phash)
     assert similar and sim == 100.0 and hashing.get_phash_similarity(phash, phash) == 100.0
+
+
+@pytest.mark.gpu
+def test_decode_feed_pool_matches_serial(tmp_path):
+    """Vpdq.computeHashes: several clips decoded by a host thread pool, every hasher feeding the
+    device's one submission service -> the same hashes as one computeHash after another, in input order."""
+    clips = []
+    for k in range(6):
+        clip = tmp_path / f"clip{k}.mkv"
+        write_clip(clip, n_frames=30 + 10 * k, size=(320 + 16 * k, 240))
+        clips.append(clip)
+    serial = [hashing.compute_phash(c) for c in clips]
+    pooled = hashing.compute_phashes(clips, num_threads=4)
+    assert [p.bytes for p in pooled] == [s.bytes for s in serial]
+    assert [p.bytes for p in pooled] == [oracle.video_hash(decoded_reference(c)) for c in clips]

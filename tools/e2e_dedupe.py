@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--clips", type=int, default=1000)
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips hashed by the CPU oracle for the baseline rate")
+    ap.add_argument("--cpu-query-clips", type=int, default=64, help="query clips searched by the CPU oracle (dedupe baseline)")
+    ap.add_argument("--out", type=str, default="", help="also write the JSON line to this file")
     args = ap.parse_args()
     rank, world, local = hdist.init()
     dev = torch.device("cuda", local)
@@ -102,7 +104,39 @@ def main():
             out["cpu_sample"] = f"{args.cpu_clips} clips x {args.frames} frames, oracle port"
             got = table[: args.cpu_clips].reshape(-1, 32).cpu().numpy()
             out["parity_vs_oracle"] = bool((got == ref_h).all() and (qual[: args.cpu_clips].reshape(-1).cpu().numpy() == ref_q).all())
-        print(json.dumps(out), flush=True)
+            # the CPU side of the dedupe: brute-force search of a SAMPLE of query clips against the whole table on all
+            # cores (what the reference's search_file loop computes, dedup.py:445-502), extrapolated to all clips
+            flat_h = flat.cpu().numpy()
+            off_h = offsets.cpu().numpy()
+            nq = min(args.cpu_query_clips, args.clips)
+            from concurrent.futures import ThreadPoolExecutor
+
+            def cpu_search(qv):  # (the C oracle releases the GIL: one query clip per host thread)
+                q = flat_h[off_h[qv]:off_h[qv + 1]]
+                if len(q) == 0:
+                    return set()
+                m = oracle.video_matched(q, flat_h, off_h, 31)
+                dist = (100 - (100 * m.astype(np.int64)) // len(q)) + 1
+                return {(qv, int(v)) for v in np.flatnonzero((m > 0) & (dist <= 51)) if int(v) != qv}
+
+            t0 = time.perf_counter()
+            cpu_rows = set()
+            with ThreadPoolExecutor(cores) as ex:
+                for rows in ex.map(cpu_search, range(nq)):
+                    cpu_rows |= rows
+            dt = time.perf_counter() - t0
+            out["cpu_dedupe_s_sample"] = dt
+            out["cpu_dedupe_sample"] = f"{nq} of {args.clips} query clips vs the whole table, oracle port"
+            out["cpu_dedupe_s_extrapolated"] = dt * args.clips / max(1, nq)
+            out["cpu_total_s_extrapolated"] = args.clips * args.frames / out["cpu_frames_per_s"] + out["cpu_dedupe_s_extrapolated"]
+            out["gpu_total_s"] = out["hash_s"] + out["dedupe_s"]
+            out["speedup_vs_cpu_extrapolated"] = out["cpu_total_s_extrapolated"] / out["gpu_total_s"]
+            out["dedupe_rows_match_cpu_sample"] = bool({(x, y) for x, y in found if x < nq} == cpu_rows)
+        line = json.dumps(out)
+        print(line, flush=True)
+        if args.out:
+            Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+            Path(args.out).write_text(line + "\n")
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -1,25 +1,26 @@
-"""Frames/s through the reference-shaped streaming API: VideoHasher.hash_frame(bytes) per frame, then finish()."""
+"""Frames/s through the reference-shaped streaming API (vpdq.VideoHasher.hash_frame(bytes) per frame, one hasher per
+video, finish() per video) -- the same measurement bench.py reports under e2e.video_hasher_api, on its own:
+  [VPDQ_B200_COPY_THREADS=..] [VPDQ_B200_LAUNCH_MIN=..] python tools/hasher_rate.py"""
+import json
+import os
 import sys
-import time
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-import numpy as np
+import torch
 
-from hydrus_video_deduplicator_b200 import vpdq
+import bench
+from hydrus_video_deduplicator_b200 import device as dev_api
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-rng = np.random.default_rng(0)
-frames = [rng.integers(0, 256, 512 * 512 * 3, dtype=np.uint8).tobytes() for _ in range(64)]
-h = vpdq.VideoHasher(1, 512, 512, 0)
-for k in range(64):
-    h.hash_frame(frames[k])
-h.finish()
-h = vpdq.VideoHasher(1, 512, 512, 0)
-t0 = time.perf_counter()
-for k in range(n):
-    h.hash_frame(frames[k & 63])
-t1 = time.perf_counter()
-ph = h.finish()
-t2 = time.perf_counter()
-print(f"hash_frame x {n}: {n / (t1 - t0):.0f} frames/s pushing, {n / (t2 - t0):.0f} frames/s incl. finish(); kept {len(ph)}")
+dev = torch.device("cuda", 0)
+pool0 = bench.device_frames(torch, 128, dev, seed=1000)
+
+
+class A:
+    pass
+
+
+out = bench.hasher_api_section(torch, dev_api, pool0, 0, torch.cuda.synchronize, lambda x: x, 1, A())
+env = {k: v for k, v in os.environ.items() if k.startswith("VPDQ_B200_")}
+print(json.dumps({"env": env, **{k: (round(v["frames/s"]), v["bit_identical_to_device_path"]) for k, v in out.items()
+                                 if isinstance(v, dict)}}))
