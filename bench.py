@@ -571,11 +571,15 @@ def hasher_api_section(torch, dev_api, pool0, local, sync_all, max_over_ranks, w
 
     out = {"api": "vpdq.VideoHasher.hash_frame(bytes) x n, finish(); one hasher per video; frames are pageable Python "
                   "bytes", "n_gpus": world}
+    from hydrus_video_deduplicator_b200 import _ffi
+
     run_videos(2, 40, 0, False)  # warm the service (arena allocation, threads)
     for name, n_frames, n_videos, threads in (("300_frame_videos", 300, 10, 1), ("10_frame_videos", 10, 300, 1),
                                               ("10_frame_videos_4_threads", 10, 300, 4)):
         results = [True] * threads
         sync_all()
+        st0 = _ffi.service_stats(local)
+        t_push = [0.0] * threads
         t0 = time.perf_counter()
         if threads == 1:
             results[0] = run_videos(n_videos, n_frames, 0, True)
@@ -589,8 +593,14 @@ def hasher_api_section(torch, dev_api, pool0, local, sync_all, max_over_ranks, w
                 th.join()
         dt = max_over_ranks(time.perf_counter() - t0)
         total = (n_videos // threads) * threads * n_frames
+        st1 = _ffi.service_stats(local)
+        ds = {k: st1[k] - st0[k] for k in st1}
         out[name] = {"frames/s": world * total / dt, "videos": (n_videos // threads) * threads, "frames_per_video": n_frames,
-                     "caller_threads": threads, "bit_identical_to_device_path": bool(all(results))}
+                     "caller_threads": threads, "bit_identical_to_device_path": bool(all(results)),
+                     "service": {"frames_per_launch": ds["frames_launched"] / max(1, ds["launches"]),
+                                 "frames_per_upload": ds["frames_launched"] / max(1, ds["upload_calls"]),
+                                 "push_blocked_share": ds["push_blocked_ns"] / 1e9 / dt / threads,
+                                 "finish_wait_share": ds["finish_wait_ns"] / 1e9 / dt / threads}}
     return out
 
 

@@ -11,7 +11,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libvpdq_b200.so"
+# (VPDQ_B200_LIB: development only -- time an alternative build of the same sources, tools/variants.sh)
+LIB_PATH = Path(os.environ["VPDQ_B200_LIB"]) if os.environ.get("VPDQ_B200_LIB") else _PKG / "libvpdq_b200.so"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, -1, -2, -3, -4, -5
 FRAME_DIM = 512
@@ -63,6 +64,7 @@ PROTOTYPES = {
     "vpdq_b200_hasher_push": (C.c_int, [_vp, _vp, C.c_int64]),
     "vpdq_b200_hasher_push_nocopy": (C.c_int, [_vp, _vp, C.c_int64]),
     "vpdq_b200_hasher_consumed": (C.c_int, [_vp, _i64p]),
+    "vpdq_b200_service_stats": (C.c_int, [C.c_int, C.c_int, _i64p]),
     "vpdq_b200_hasher_pushed": (C.c_int, [_vp, _i64p]),
     "vpdq_b200_hasher_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _i64p, _vp, _vp]),
     "vpdq_b200_hasher_destroy": (C.c_int, [_vp]),
@@ -126,6 +128,13 @@ def debug_flags(device: int = 0) -> int:
     f = C.c_int(0)
     check(lib().vpdq_b200_debug_flags(int(device), C.byref(f)))
     return int(f.value)
+
+
+def service_stats(device: int = 0, channels: int = 3) -> dict:
+    out = (C.c_int64 * 8)()
+    check(lib().vpdq_b200_service_stats(int(device), int(channels), out))
+    keys = ("frames_pushed", "upload_calls", "launches", "frames_launched", "push_blocked_ns", "finish_wait_ns", "largest_launch")
+    return dict(zip(keys, list(out)[:7]))
 
 
 def default_device() -> int:

@@ -514,6 +514,15 @@ int vpdq_b200_hasher_consumed(vpdq_b200_hasher* h, int64_t* n) {
     return VPDQ_B200_OK;
 }
 
+int vpdq_b200_service_stats(int device, int channels, int64_t* out) {
+    if (!out || device < 0 || device >= 64) return VPDQ_B200_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    ServiceSlot& slot = g_services[device][channels == 1];
+    std::lock_guard<std::mutex> lk(slot.mu);
+    if (slot.svc) slot.svc->stats(out);
+    return VPDQ_B200_OK;
+}
+
 int vpdq_b200_hasher_pushed(vpdq_b200_hasher* h, int64_t* n) {
     if (!h || !n) return VPDQ_B200_ERR_INVALID;
     std::lock_guard<std::mutex> lk(h->st.mu);

@@ -151,10 +151,15 @@ class HashService {
             int64_t c;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                while (!stop_ && broken_ == 0 && head_ - tail_.load(std::memory_order_acquire) >= cfg_.arena_frames) {
-                    ++space_waiters_;
-                    cv_space_.wait(lk);  // back-pressure: the ring is full (vpdqpy.py:115-117)
-                    --space_waiters_;
+                if (head_ - tail_.load(std::memory_order_acquire) >= cfg_.arena_frames) {
+                    const auto b0 = std::chrono::steady_clock::now();
+                    while (!stop_ && broken_ == 0 && head_ - tail_.load(std::memory_order_acquire) >= cfg_.arena_frames) {
+                        ++space_waiters_;
+                        cv_space_.wait(lk);  // back-pressure: the ring is full (vpdqpy.py:115-117)
+                        --space_waiters_;
+                    }
+                    ns_push_blocked_ += std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                            std::chrono::steady_clock::now() - b0).count();
                 }
                 if (stop_) return -1;
                 if (broken_) return broken_;
@@ -220,12 +225,26 @@ class HashService {
         ++h->waiters;
         while (h->done < h->pushed && h->error == 0) h->cv.wait(lk);
         --h->waiters;
+        ns_wait_ += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         return h->error;
     }
 
     int broken() {
         std::lock_guard<std::mutex> lk(mu_);
         return broken_;
+    }
+
+    // counters since start(): [0] frames pushed, [1] upload calls, [2] launches, [3] frames launched,
+    // [4] ns pushes spent blocked on a full ring, [5] ns finish() calls spent waiting, [6] largest launch
+    void stats(int64_t out[8]) const {
+        out[0] = head_pub_.load();
+        out[1] = n_uploads_.load();
+        out[2] = n_launches_.load();
+        out[3] = n_launched_frames_.load();
+        out[4] = ns_push_blocked_.load();
+        out[5] = ns_wait_.load();
+        out[6] = max_launch_seen_.load();
+        out[7] = 0;
     }
 
   private:
@@ -365,6 +384,7 @@ class HashService {
                     const int rc = dev_->upload(d_frames_ + (size_t)(c % A) * fb, h_frames_ + (size_t)(c % A) * fb,
                                                 (size_t)(e - c) * fb);
                     if (rc) fail(rc);
+                    ++n_uploads_;
                     c = e;
                 }
                 for (int64_t k = uploaded; k < u; ++k) {  // the sources of these frames are no longer needed
@@ -390,6 +410,9 @@ class HashService {
                     fail(rc);
                 } else {
                     inflight.push_back(L);
+                    ++n_launches_;
+                    n_launched_frames_ += e - launched;
+                    if (e - launched > max_launch_seen_.load()) max_launch_seen_ = e - launched;
                 }
                 launched = e;
                 progressed = true;
@@ -444,6 +467,9 @@ class HashService {
     std::deque<Task> tasks_;
     int sleeping_workers_ = 0;
     std::atomic<bool> stop_atomic_{false};
+
+    std::atomic<int64_t> n_uploads_{0}, n_launches_{0}, n_launched_frames_{0}, ns_push_blocked_{0}, ns_wait_{0},
+        max_launch_seen_{0};
 
     std::thread pump_;
     std::vector<std::thread> workers_;

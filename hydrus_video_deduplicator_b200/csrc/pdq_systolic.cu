@@ -23,7 +23,10 @@
 namespace vpdq {
 using namespace vpdq_sys;
 
-constexpr int kSysWarps = 8;
+#ifndef VPDQS_WARPS
+#define VPDQS_WARPS 8
+#endif
+constexpr int kSysWarps = VPDQS_WARPS;  // warps (= frames in flight) per SM: bounded by the raw rings in shared memory
 constexpr int kSysThreads = 32 * kSysWarps;
 
 template <int CH>
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
             if (lane == 0) {
                 const uint32_t bar = bar0 + 8 * (E & 1);
                 mbar_expect_tx(bar, kGroups * R::kBoxBytes);
-                tma_load_3d(ring + (E & 3) * (kGroups * R::kBoxBytes), &tmap3, 0,
+                tma_load_3d(ring + (E % kBoxSlots) * (kGroups * R::kBoxBytes), &tmap3, 0,
                             first_row + ev_f * 512 + ev_r - View3<CH>::kBackRows, 0, bar);
             }
             __syncwarp();
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         uint32_t w[R::kWords];
         {
             const int a = t + lane_a;
-            const uint32_t off = L.img_next ? lane_base + (a & 12) * (kGroups * R::kBoxBytes / 4) + (a & 3) * R::kSegPitch : zeros;
+            const uint32_t off = L.img_next ? lane_base + ((a >> 2) % kBoxSlots) * (kGroups * R::kBoxBytes) + (a & 3) * R::kSegPitch : zeros;
             const bool nimg = (unsigned)f0n < (unsigned)F && r0n < kImageRows;
             const uint32_t last31 = nimg ? grp0_base + ring_row_offset<CH>(0, t + 2) : zeros;
             const uint32_t last = lane == 31 ? last31 : off + 16 * (R::kChunks - 1);

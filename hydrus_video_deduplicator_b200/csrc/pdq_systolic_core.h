@@ -147,7 +147,11 @@ VPDQS_HD F2 edge3(F2 v) {  // the same on a packed pair (no multiply feeds an ad
 constexpr int kCols = 16;            // image columns per lane
 constexpr int kStepsPerFrame = 516;  // 512 image rows + 4 zero rows
 constexpr int kImageRows = 512;
-constexpr int kRing = 16;            // stream rows per group ring
+#ifndef VPDQS_RING_ROWS
+#define VPDQS_RING_ROWS 16
+#endif
+constexpr int kRing = VPDQS_RING_ROWS;  // stream rows per group ring: 16 (4 box slots, 8 steps of TMA lead) or 12 (3, 4)
+constexpr int kBoxSlots = kRing / 4;
 constexpr int kBoxRows = 4;          // stream rows per TMA box
 constexpr int kGroupLanes = 4;
 constexpr int kGroups = 32 / kGroupLanes;  // 8
@@ -156,7 +160,8 @@ constexpr int kGroups = 32 / kGroupLanes;  // 8
 #endif
 constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4 or 8 (see LaneState)
 constexpr int kFirstStep = -8;       // the step loop starts here (a multiple of 8; steps < 0 only prepare lane 0's first row)
-constexpr int kIssueLead = 10;       // ISSUE(E) at step 4 E - 10
+constexpr int kIssueLead = kRing - 6; // ISSUE(E) at step 4 E - 10 (ring of 16 rows; 4 E - 6 with 12): the earliest step at
+                                     // which no lane still reads the box slot being refilled
 constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
                                      // computed one step ahead, as filler work for the serial chains)
 constexpr int kEventPhase = 2;       // both happen in the steps with (step & 3) == 2
@@ -187,7 +192,7 @@ VPDQS_HD int ring_group_offset(int g) { return (kGroups - 1 - g) * Raw<CH>::kBox
 template <int CH>
 VPDQS_HD int ring_row_offset(int g, int s) {
     const int a = s + kGroupLanes * g;
-    return ((a >> 2) & 3) * (kGroups * Raw<CH>::kBoxBytes) + (a & 3) * Raw<CH>::kSegPitch;
+    return ((a >> 2) % kBoxSlots) * (kGroups * Raw<CH>::kBoxBytes) + (a & 3) * Raw<CH>::kSegPitch;
 }
 // byte offset (inside the warp's ring) of the window of `lane` for stream row s
 template <int CH>
@@ -197,7 +202,7 @@ VPDQS_HD int ring_offset(int lane, int s) {
 // the TMA box of event E for group g: first stream row (may be negative = nothing to load)
 VPDQS_HD int box_first_row(int E, int g) { return kBoxRows * E - kGroupLanes * g; }
 template <int CH>
-VPDQS_HD int box_ring_offset(int g, int E) { return (E & 3) * (kGroups * Raw<CH>::kBoxBytes) + ring_group_offset<CH>(g); }
+VPDQS_HD int box_ring_offset(int g, int E) { return (E % kBoxSlots) * (kGroups * Raw<CH>::kBoxBytes) + ring_group_offset<CH>(g); }
 template <int CH>
 VPDQS_HD int box_x(int g) { return g * Raw<CH>::kSegBytes; }
 // The 3-D view of the batch that makes all 8 boxes of an event one TMA box: element (x, y, g') lives at byte

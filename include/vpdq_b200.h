@@ -125,6 +125,10 @@ VPDQ_B200_API int vpdq_b200_hasher_push(vpdq_b200_hasher* h, const uint8_t* h_fr
 VPDQ_B200_API int vpdq_b200_hasher_push_nocopy(vpdq_b200_hasher* h, const uint8_t* h_frames, int64_t n_frames);
 /* number of leading frames (in push order, since the last finish) whose source memory is no longer needed */
 VPDQ_B200_API int vpdq_b200_hasher_consumed(vpdq_b200_hasher* h, int64_t* n);
+/* counters of the submission service of (device, channels) since it started, for tuning and reports:
+ * out[0] frames pushed, [1] upload (H2D) calls, [2] kernel launch groups, [3] frames launched, [4] ns pushes spent blocked on
+ * a full ring, [5] ns finish() calls spent waiting, [6] largest launch, [7] reserved */
+VPDQ_B200_API int vpdq_b200_service_stats(int device, int channels, int64_t* out /* [8] */);
 /* total frames pushed so far (upper bound for finish's capacity) */
 VPDQ_B200_API int vpdq_b200_hasher_pushed(vpdq_b200_hasher* h, int64_t* n);
 /* Writes kept hashes (quality >= quality_keep) to h_hashes [cap][32]; *n_kept = number kept.

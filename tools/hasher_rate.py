@@ -22,5 +22,6 @@ class A:
 
 out = bench.hasher_api_section(torch, dev_api, pool0, 0, torch.cuda.synchronize, lambda x: x, 1, A())
 env = {k: v for k, v in os.environ.items() if k.startswith("VPDQ_B200_")}
-print(json.dumps({"env": env, **{k: (round(v["frames/s"]), v["bit_identical_to_device_path"]) for k, v in out.items()
+print(json.dumps({"env": env, **{k: (round(v["frames/s"]), v["bit_identical_to_device_path"],
+                                     {a: round(b, 3) for a, b in v["service"].items()}) for k, v in out.items()
                                  if isinstance(v, dict)}}))
