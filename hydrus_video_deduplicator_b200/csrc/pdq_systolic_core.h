@@ -243,10 +243,9 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
 // overflows the 32 KB L1.5 instruction cache ("no_instructions" stalls 3 % -> 19 %, 2 % slower overall), so the
 // product builds kBody = 4 (one history set; ptxas inserts the copies).
 struct LaneState {
-    F2 s2[2][kCols / 2];      // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair; read from
-                              // s2[step & 1], written to the other set.  At the start of a step they are ALSO the P2
-                              // outputs of the previous step, which P3 consumes in this one (one value for both: see the
-                              // tail of lane_step for the divisor-3 rows)
+    F2 s2[kCols / 2];         // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start
+                              // of a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
+                              // (one value for both: see the tail of lane_step for the divisor-3 rows)
     F2 h2[kBody / 4][4][kCols / 2];   // P2 histories (the last four inputs): the value written at step u is h2[set(u)][u & 3]
     F2 x[2][kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..) in x[step & 1], computed during the previous step
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
@@ -259,7 +258,7 @@ struct LaneState {
     VPDQS_HD void init(int lane) {
         VPDQS_UNROLL
         for (int p = 0; p < kCols / 2; ++p) {
-            s2[0][p] = s2[1][p] = f2_splat(0.0f);
+            s2[p] = f2_splat(0.0f);
             VPDQS_UNROLL
             for (int j = 0; j < 4; ++j) h2[0][j][p] = h2[kBody / 4 - 1][j][p] = f2_splat(0.0f);
             x[0][p] = x[1][p] = f2_splat(0.0f);
@@ -280,25 +279,35 @@ struct LaneState {
 VPDQS_HD constexpr int hist_set(int U8) { return kBody == 8 ? ((((U8 + 8) & 7) >> 2) & 1) ^ 1 : 0; }
 VPDQS_HD constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
 
-// M = 2^23 + byte: the byte at offset b of the little-endian word array spliced into the mantissa of 2^23 (PRMT)
+// u8 -> fp32 product without an I2F: the byte is spliced into the mantissa of a power of two, M = 2^k + byte exactly, and
+// fma(c, M, -c * 2^k) = RN(c * byte) -- bit-identical to __fmul_rn(c, (float)byte) (c * 2^k is exact).  Bytes 2 and 3 of a
+// word go to the low mantissa byte of 2^23 with one PRMT (half-rate pipe); bytes 0 and 1 stay where they are under a
+// mask -- one LOP3 (full rate): byte 0 in the mantissa of 2^23, byte 1 in that of 2^15 (its bits then weigh 2^0..2^7).
+#ifndef VPDQS_LOP3_SPLICE
+#define VPDQS_LOP3_SPLICE 1
+#endif
+VPDQS_HD constexpr float magic_base(int b) { return (VPDQS_LOP3_SPLICE && (b & 3) == 1) ? 32768.0f : 8388608.0f; }
 template <int N>
 VPDQS_HD float magic_at(const uint32_t (&w)[N], int b) {
-    return bits_to_float(byte_splice(w[b >> 2], b & 3));
+    const uint32_t word = w[b >> 2];
+    if (VPDQS_LOP3_SPLICE && (b & 3) == 0) return bits_to_float((word & 0x000000FFu) | 0x4B000000u);  // 2^23 + byte
+    if (VPDQS_LOP3_SPLICE && (b & 3) == 1) return bits_to_float((word & 0x0000FF00u) | 0x47000000u);  // 2^15 + byte
+    return bits_to_float(byte_splice(word, b & 3));                                                    // 2^23 + byte
 }
 
 // luma of the two pixels whose first bytes sit at byte offsets b0 and b0 + CH of w, as one packed pair.
-// u8 -> fp32 product without an I2F: fma(c, M, -c * 2^23) = RN(c * b), bit-identical to __fmul_rn(c, (float)b)
-// (c * 2^23 is exact).  CH == 1: the same three-term expression on one byte (SURVEY.md 8 note a-1).
+// CH == 1: the same three-term expression on one byte (SURVEY.md 8 note a-1).
 template <int CH, int N>
 VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
-    const float cr = 0.299f, cg = 0.587f, cb = 0.114f, two23 = 8388608.0f;
+    const float cr = 0.299f, cg = 0.587f, cb = 0.114f;
     const int p0 = b0, p1 = b0 + CH;
+    const int g0 = CH == 3 ? p0 + 1 : p0, g1 = CH == 3 ? p1 + 1 : p1, u0 = CH == 3 ? p0 + 2 : p0, u1 = CH == 3 ? p1 + 2 : p1;
     const F2 mr{magic_at(w, p0), magic_at(w, p1)};
-    const F2 mg = CH == 3 ? F2{magic_at(w, p0 + 1), magic_at(w, p1 + 1)} : mr;
-    const F2 mb = CH == 3 ? F2{magic_at(w, p0 + 2), magic_at(w, p1 + 2)} : mr;
-    const F2 r = f2_fma(f2_splat(cr), mr, f2_splat(-(cr * two23)));
-    const F2 g = f2_fma(f2_splat(cg), mg, f2_splat(-(cg * two23)));
-    const F2 b = f2_fma(f2_splat(cb), mb, f2_splat(-(cb * two23)));
+    const F2 mg = CH == 3 ? F2{magic_at(w, g0), magic_at(w, g1)} : mr;
+    const F2 mb = CH == 3 ? F2{magic_at(w, u0), magic_at(w, u1)} : mr;
+    const F2 r = f2_fma(f2_splat(cr), mr, F2{-(cr * magic_base(p0)), -(cr * magic_base(p1))});
+    const F2 g = f2_fma(f2_splat(cg), mg, F2{-(cg * magic_base(g0)), -(cg * magic_base(g1))});
+    const F2 b = f2_fma(f2_splat(cb), mb, F2{-(cb * magic_base(u0)), -(cb * magic_base(u1))});
     return f2_add(f2_add(r, g), b);  // (0.299 R + 0.587 G) + 0.114 B
 }
 
@@ -335,11 +344,11 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         const float v1 = row_feed(c1, x.y);
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
-        const F2 old = L.h2[PH][J][p], prev = L.s2[PX][p];
+        const F2 old = L.h2[PH][J][p], prev = L.s2[p];
         F2 s = f2_add(prev, v);
         s = f2_sub(s, old);
         L.h2[PHW][J][p] = v;
-        L.s2[PX ^ 1][p] = s;
+        L.s2[p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
         const float u0 = row_feed(c3, prev.x);
@@ -375,7 +384,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         // running sum (its subtractions are all of zeros there).
         if (r == 2 || r == kImageRows) {
             VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[PX ^ 1][p] = edge3(L.s2[PX ^ 1][p]);
+            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = edge3(L.s2[p]);
         }
         if (r == 2) {  // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
             L.s4 = f2_splat(0.0f);
@@ -384,7 +393,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         if (r == 3) {
             VPDQS_UNROLL
             for (int p = 0; p < kCols / 2; ++p)
-                L.s2[PX ^ 1][p] = f2_add(f2_add(f2_add(L.h2[hist_set(T8 - 3)][hist_slot(T8 - 3)][p],
+                L.s2[p] = f2_add(f2_add(f2_add(L.h2[hist_set(T8 - 3)][hist_slot(T8 - 3)][p],
                                                L.h2[hist_set(T8 - 2)][hist_slot(T8 - 2)][p]),
                                         L.h2[hist_set(T8 - 1)][hist_slot(T8 - 1)][p]),
                                  L.h2[hist_set(T8)][hist_slot(T8)][p]);
@@ -396,7 +405,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
             L.r = 0;                    // rows, the sums hold rounding residue
             ++L.f;
             VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[PX ^ 1][p] = f2_splat(0.0f);
+            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = f2_splat(0.0f);
         }
     }
 }
