@@ -42,8 +42,11 @@ struct Config {
     int max_launch = 2048;    // frames per kernel launch
     int max_inflight = 3;     // launches in flight
     int launch_min = 64;      // launch as soon as this many uploaded frames are waiting; fewer only when a finish() is
-                              // waiting for them (a launch has a fixed latency of ~0.2 ms: launching frame by frame as
-                              // they trickle in would serialise a short video into several of those)
+                              // waiting for them and they are ALL uploaded (a launch has a fixed latency of ~0.2 ms:
+                              // launching frame by frame as they trickle in would serialise a short video into
+                              // several of those)
+    int upload_min = 8;       // upload runs of at least this many frames while more are still being copied (one
+                              // cudaMemcpyAsync per frame would make the pump thread the bottleneck)
     int spin_us = 2000;       // how long idle threads poll before they sleep (a hashing session pushes continuously)
 };
 
@@ -376,7 +379,9 @@ class HashService {
             const int64_t h = head_pub_.load(std::memory_order_acquire);
             int64_t u = uploaded;
             while (u < h && slots_[u % A].parts_left.load(std::memory_order_acquire) == 0) ++u;
-            if (u > uploaded) {
+            const bool ring_full = h - tail_.load(std::memory_order_acquire) >= A;
+            if (u > uploaded && (u - uploaded >= cfg_.upload_min || u == h || ring_full ||
+                                 (u % A) < (uploaded % A))) {  // (a run that reaches the ring's end goes at once)
                 int64_t c = uploaded;
                 while (c < u) {
                     int64_t e = c - (c % A) + A;  // ring wrap
@@ -397,9 +402,10 @@ class HashService {
             // (3) launch over what is uploaded: when enough frames wait, or a finish() waits for some of them, or pushes
             // are blocked on a full ring; at most max_inflight launches in flight
             const int64_t waiting = uploaded - launched;
-            const bool flush = flush_upto_.load(std::memory_order_acquire) > launched;
+            const int64_t want = flush_upto_.load(std::memory_order_acquire);  // a finish() waits for frames below this
+            const bool flush = want > launched && uploaded >= (want < h ? want : h);
             if (waiting > 0 && (int)inflight.size() < cfg_.max_inflight &&
-                (waiting >= cfg_.launch_min || flush || head_pub_.load(std::memory_order_acquire) - tail_.load() >= A)) {
+                (waiting >= cfg_.launch_min || flush || ring_full)) {
                 int64_t e = launched - (launched % A) + A;
                 if (e > uploaded) e = uploaded;
                 if (e - launched > cfg_.max_launch) e = launched + cfg_.max_launch;

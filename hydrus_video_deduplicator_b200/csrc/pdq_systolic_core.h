@@ -283,8 +283,10 @@ VPDQS_HD constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
 // fma(c, M, -c * 2^k) = RN(c * byte) -- bit-identical to __fmul_rn(c, (float)byte) (c * 2^k is exact).  Bytes 2 and 3 of a
 // word go to the low mantissa byte of 2^23 with one PRMT (half-rate pipe); bytes 0 and 1 stay where they are under a
 // mask -- one LOP3 (full rate): byte 0 in the mantissa of 2^23, byte 1 in that of 2^15 (its bits then weigh 2^0..2^7).
+// (Measured on B200: the LOP3 form is 8 % SLOWER end to end -- the per-position offsets stop the FFMA2 constants
+// from being shared -- so the product uses PRMT for all four positions; the switch stays for the record.)
 #ifndef VPDQS_LOP3_SPLICE
-#define VPDQS_LOP3_SPLICE 1
+#define VPDQS_LOP3_SPLICE 0
 #endif
 VPDQS_HD constexpr float magic_base(int b) { return (VPDQS_LOP3_SPLICE && (b & 3) == 1) ? 32768.0f : 8388608.0f; }
 template <int N>
