@@ -379,9 +379,9 @@ class HashService {
             const int64_t h = head_pub_.load(std::memory_order_acquire);
             int64_t u = uploaded;
             while (u < h && slots_[u % A].parts_left.load(std::memory_order_acquire) == 0) ++u;
-            const bool ring_full = h - tail_.load(std::memory_order_acquire) >= A;
-            if (u > uploaded && (u - uploaded >= cfg_.upload_min || u == h || ring_full ||
-                                 (u % A) < (uploaded % A))) {  // (a run that reaches the ring's end goes at once)
+            // (a full ring is the normal state when the caller pushes faster than the pipeline drains: every slot is
+            //  allocated and being copied, so runs of upload_min keep coming; only the last few frames rely on u == h)
+            if (u > uploaded && (u - uploaded >= cfg_.upload_min || u == h)) {
                 int64_t c = uploaded;
                 while (c < u) {
                     int64_t e = c - (c % A) + A;  // ring wrap
@@ -404,8 +404,10 @@ class HashService {
             const int64_t waiting = uploaded - launched;
             const int64_t want = flush_upto_.load(std::memory_order_acquire);  // a finish() waits for frames below this
             const bool flush = want > launched && uploaded >= (want < h ? want : h);
+            // a full ring in which everything is already uploaded cannot grow the launch any further
+            const bool stuck = uploaded == h && h - tail_.load(std::memory_order_acquire) >= A;
             if (waiting > 0 && (int)inflight.size() < cfg_.max_inflight &&
-                (waiting >= cfg_.launch_min || flush || ring_full)) {
+                (waiting >= cfg_.launch_min || flush || stuck)) {
                 int64_t e = launched - (launched % A) + A;
                 if (e > uploaded) e = uploaded;
                 if (e - launched > cfg_.max_launch) e = launched + cfg_.max_launch;

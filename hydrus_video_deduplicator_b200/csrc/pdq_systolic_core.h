@@ -53,6 +53,7 @@
 #else
 #define VPDQS_HD inline
 #endif
+#define VPDQS_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #if defined(__CUDA_ARCH__)
 #define VPDQS_UNROLL _Pragma("unroll")
 #else
@@ -376,7 +377,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
                     bitkeep(~last, c3.h3)};
     L.r = r + 1;
     // ---- tail: the rare rows ----
-    if ((unsigned)(r - 2) < 2u || r >= kImageRows - 2) {
+    if (VPDQS_UNLIKELY((unsigned)(r - 2) < 2u || r >= kImageRows - 2)) {
         const bool live = (unsigned)L.f < (unsigned)n_frames;
         // P2 output rows 0 (r = 2) and 510 (r = 512) have divisor 3.  The sums double as P3's input of the next step,
         // so the fix-up is done IN PLACE (no second set of registers, no copies in the common path): after row 510
