@@ -47,7 +47,9 @@ struct Config {
                               // several of those)
     int upload_min = 8;       // upload runs of at least this many frames while more are still being copied (one
                               // cudaMemcpyAsync per frame would make the pump thread the bottleneck)
-    int spin_us = 2000;       // how long idle threads poll before they sleep (a hashing session pushes continuously)
+    int spin_us = 2000;       // how long the pump and a finish() poll before they sleep (a hashing session pushes
+                              // continuously; a futex sleep + wake-up costs ~50 us per hop)
+    int worker_spin_us = 200; // the same for the copy workers (several of them: keep their idle polling short)
 };
 
 // memcpy into the pinned ring with non-temporal stores: the destination is read next by the DMA engine, not by a CPU,
@@ -290,7 +292,7 @@ class HashService {
             // spin briefly (the next frame of a video usually follows within microseconds), then sleep
             bool got = false;
             const auto t0 = std::chrono::steady_clock::now();
-            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(cfg_.spin_us)) {
+            while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(cfg_.worker_spin_us)) {
                 if (run_one_task()) {
                     got = true;
                     break;
@@ -443,10 +445,7 @@ class HashService {
                 }
                 continue;
             }
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (stop_ && inflight.empty()) return;
-            }
+            if (stop_flag() && inflight.empty()) return;  // (no lock here: this loop spins while work is outstanding)
             dev_->idle_pause(!inflight.empty());
         }
     }

@@ -51,14 +51,17 @@ def main():
     t_hash = 0.0
     local_hashes = torch.zeros((len(mine), args.frames, 32), dtype=torch.uint8, device=dev)
     local_quality = torch.zeros((len(mine), args.frames), dtype=torch.int32, device=dev)
-    for n, k in enumerate(mine):
-        frames = clip_frames(int(k), args.clips, args.frames, dev)
+    group = max(1, 8192 // args.frames)  # clips hashed per launch pair (the frames of one group live in HBM together)
+    for n0 in range(0, len(mine), group):
+        ks = mine[n0:n0 + group]
+        frames = torch.cat([clip_frames(int(k), args.clips, args.frames, dev) for k in ks])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         h, q = device.hash_frames(frames)
         torch.cuda.synchronize()
         t_hash += time.perf_counter() - t0
-        local_hashes[n], local_quality[n] = h, q
+        local_hashes[n0:n0 + len(ks)] = h.view(len(ks), args.frames, 32)
+        local_quality[n0:n0 + len(ks)] = q.view(len(ks), args.frames)
     # exchange: every rank gets the whole table, in clip order
     parts_h = hdist.all_gather_varlen(local_hashes.reshape(len(mine), -1))
     parts_q = hdist.all_gather_varlen(local_quality)
