@@ -39,9 +39,9 @@ constexpr int kDJ = 68;  // pitch of the D / T rows: 128-bit k-chunks of 8 conse
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 
-__global__ void __launch_bounds__(256) k5_finalize(const float* __restrict__ a64, uint8_t* __restrict__ hashes,
-                                                   int32_t* __restrict__ quality, float* __restrict__ a64_dbg,
-                                                   float* __restrict__ b16_dbg) {
+__global__ void __launch_bounds__(256) k5_finalize(const float* __restrict__ a64, long long n_frames,
+                                                   uint8_t* __restrict__ hashes, int32_t* __restrict__ quality,
+                                                   float* __restrict__ a64_dbg, float* __restrict__ b16_dbg) {
     __shared__ __align__(16) float A[kDec][kDec];  // decimated 64x64 plane
     __shared__ __align__(16) float Dt[kDec][16];   // Dt[k][i] = D[i][k]
     __shared__ __align__(16) float Dj[16][kDJ];    // D[j][k]
@@ -51,13 +51,15 @@ __global__ void __launch_bounds__(256) k5_finalize(const float* __restrict__ a64
     __shared__ int med_key;
 
     const int t = threadIdx.x;
-    const int64_t f = blockIdx.x;
 
+    // the two copies of the DCT table are filled once per CTA; a CTA then walks over frames (persistent grid)
 #pragma unroll
     for (int e = t; e < 16 * 64; e += 256) {
         Dj[e >> 6][e & 63] = __ldg(g_dct + e);
         Dt[e >> 4][e & 15] = __ldg(g_dct + (e & 15) * 64 + (e >> 4));  // consecutive lanes -> consecutive words of Dt
     }
+#pragma unroll 1
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
     if (t == 0) {
         g_sum = 0u;
         med_key = INT_MIN;
@@ -164,6 +166,8 @@ __global__ void __launch_bounds__(256) k5_finalize(const float* __restrict__ a64
         const int q = (int)(g_sum / 90u);
         quality[f] = q > 100 ? 100 : q;
     }
+    __syncthreads();  // A, T, B, g_sum, med_key are reused by the next frame
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -209,7 +213,12 @@ int pdq_finalize_launch(const float* d_a64, int64_t n_frames, uint8_t* d_hashes,
     if (n_frames == 0) return VPDQ_B200_OK;
     const int rc = pdq_upload_tables();
     if (rc) return rc;
-    k5_finalize<<<(unsigned)n_frames, 256, 0, stream>>>(d_a64, d_hashes, d_quality, d_a64_dbg, d_b16_dbg);
+    int dev = 0, sms = 148;
+    VPDQ_CUDA(cudaGetDevice(&dev));
+    VPDQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t resident = (int64_t)sms * 7;  // 7 CTAs of 256 threads / 33 KB of shared memory fit an SM
+    const unsigned grid = (unsigned)(n_frames < resident ? n_frames : resident);
+    k5_finalize<<<grid, 256, 0, stream>>>(d_a64, (long long)n_frames, d_hashes, d_quality, d_a64_dbg, d_b16_dbg);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;
