@@ -22,3 +22,8 @@ print("luma", d["luma_frames"])
 PY
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 cut -c1-300 gpurun_out/bench_reference.json
+# ncu: launch list of the same bench command (cold-cache, serialised: shares must agree, not absolutes) + full captures
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^(kx_|k5_|k_)' -c 80 --csv --log-file gpurun_out/launches_ncu.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-hasher-api > gpurun_out/bench_under_ncu.log 2>&1
+tail -2 gpurun_out/launches_ncu.csv | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kx_systolic_jarosz|k5_finalize' -s 4 -c 2 -o gpurun_out/prof_pdq -f python tools/prof_pdq.py 4096 > gpurun_out/prof_pdq.log 2>&1
+tail -2 gpurun_out/prof_pdq.log
