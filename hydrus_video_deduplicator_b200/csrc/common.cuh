@@ -41,9 +41,6 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
                float* d_a64, float* d_b16, void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
 // first half: luma + the four Jarosz passes + 64x64 decimation, one warp per frame (pdq_systolic.cu)
 int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream);
-// the whole hash in one persistent kernel: the same Jarosz warps + finalize warps that pick up every finished plane
-int systolic_pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, const float* d_dct,
-                        uint8_t* d_hashes, int32_t* d_quality, cudaStream_t stream);
 int systolic_debug_flags(int* flags);
 int systolic_debug_force_timeout(int value);
 int systolic_timeout_flag_async(int* h_flag, cudaStream_t stream);
@@ -51,7 +48,6 @@ int systolic_timeout_flag_async(int* h_flag, cudaStream_t stream);
 int pdq_finalize_launch(const float* d_a64, int64_t n_frames, uint8_t* d_hashes, int32_t* d_quality, float* d_a64_dbg,
                         float* d_b16_dbg, cudaStream_t stream);
 int pdq_upload_tables();  // DCT matrix -> device (once per device)
-int pdq_device_dct(const float** d_dct);  // ... and where it lives on the current device
 // the kernels' "a bounded TMA wait gave up" flag -> h_flags[0] (pinned, >= 4 ints), stream-ordered; nonzero = results
 // of the launches before it on this device are invalid.  Every host-pointer entry checks it at its synchronisation
 // point.

@@ -1,7 +1,9 @@
 // pdq_finalize.cuh -- the second half of the PDQ frame hash as a device function for 256 cooperating threads:
 // the decimated 64x64 plane -> quality, 64->16 DCT (both directions), median, 256 bits.  Used by k5_finalize
-// (pdq_kernels.cu: a whole CTA per frame, the two-kernel pipeline and the debug stages) and by the finalize warps of
-// the fused kernel (pdq_systolic.cu), which differ only in how the 256 threads synchronise.
+// (pdq_kernels.cu).  The synchronisation of the 256 threads is a parameter: an experiment ran this function in eight
+// extra "finalize warps" inside the persistent Jarosz kernel (register file re-split with setmaxnreg, planes handed over
+// through flags in shared memory) -- bit-exact, but 15 % slower than the two kernels back to back: compiled against
+// the 512-thread launch bound the Jarosz warps' code needs 12 % more instructions ("tried").
 //
 // Same arithmetic and order as the straightforward k4_colpass_finalize<true> kept in tests/legacy/pdq_lines.cu
 // (cross-checked by the parity tests), about half the instructions:
@@ -41,8 +43,7 @@ __device__ __forceinline__ void finalize_load_tables(FinalizeSmem& sm, const flo
     }
 }
 
-// One frame.  plane: 4096 floats in global memory (read with ld.global.cg: in the fused kernel they were written a
-// moment ago by other warps of this SM).  sync(): a barrier over the 256 threads.  The caller must sync() once more
+// One frame.  plane: 4096 floats in global memory.  sync(): a barrier over the 256 threads.  The caller must sync() once more
 // before the shared buffers are reused.
 template <typename Sync>
 __device__ __forceinline__ void finalize_frame(FinalizeSmem& sm, const float* __restrict__ plane, uint8_t* __restrict__ hash_out,

@@ -24,9 +24,7 @@ namespace vpdq {
 __device__ float g_dct[16 * 64];  // the 16 x 64 DCT table (coalesced fill of k5's shared copies)
 
 // ---------------------------------------------------------------------------------------------------
-// K5: the finalize step as its own kernel (pdq_finalize.cuh): persistent CTAs of 256 threads walk over frames.
-// Used by the two-kernel form of the pipeline (debug stages, vpdq_b200_pdq_jarosz_dev callers); the product's default
-// path runs the same device function in the finalize warps of the fused kernel (pdq_systolic.cu).
+// K5: the finalize step (pdq_finalize.cuh): persistent CTAs of 256 threads walk over frames.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k5_finalize(const float* __restrict__ a64, long long n_frames,
                                                    uint8_t* __restrict__ hashes, int32_t* __restrict__ quality,
@@ -72,13 +70,6 @@ int pdq_upload_tables() {
     return VPDQ_B200_OK;
 }
 
-int pdq_device_dct(const float** d_dct) {
-    void* p = nullptr;
-    VPDQ_CUDA(cudaGetSymbolAddress(&p, g_dct));
-    *d_dct = static_cast<const float*>(p);
-    return VPDQ_B200_OK;
-}
-
 // the only intermediate that touches HBM: the decimated plane, 64 x 64 fp32 per frame
 constexpr size_t kScratchPerFrame = (size_t)kDec * kDec * sizeof(float);
 
@@ -114,29 +105,11 @@ int pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, uint8_t*
         return VPDQ_B200_ERR_INVALID;
     }
     if (chunk > (1 << 21)) chunk = 1 << 21;  // TMA coordinates are 32-bit row indices
-    // (VPDQ_B200_FUSED=0: Jarosz kernel + finalize kernel instead of the fused one -- for A/B runs)
-    static const bool fused = [] {
-        const char* e = getenv("VPDQ_B200_FUSED");
-        return !(e && e[0] == '0');
-    }();
     const size_t frame_bytes = (size_t)kPlane * channels;
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const int64_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         float* a64 = static_cast<float*>(d_scratch);
-        int rc;
-        if (!d_a64 && !d_b16 && fused) {
-            // the product path: ONE persistent kernel, the finalize warps pick every plane up as it completes
-            rc = pdq_upload_tables();
-            const float* d_dct = nullptr;
-            if (rc == 0) rc = pdq_device_dct(&d_dct);
-            if (rc == 0)
-                rc = systolic_pdq_launch(d_frames + (size_t)f0 * frame_bytes, channels, nf, a64, d_dct,
-                                         d_hashes + (size_t)f0 * 32, d_quality + f0, stream);
-            if (rc) return rc;
-            continue;
-        }
-        // two kernels (debug stages): Jarosz planes, then the finalize kernel with its optional dumps
-        rc = systolic_jarosz_launch(d_frames + (size_t)f0 * frame_bytes, channels, nf, a64, stream);
+        int rc = systolic_jarosz_launch(d_frames + (size_t)f0 * frame_bytes, channels, nf, a64, stream);
         if (rc) return rc;
         rc = pdq_finalize_launch(a64, nf, d_hashes + (size_t)f0 * 32, d_quality + f0,
                                  d_a64 ? d_a64 + (size_t)f0 * 4096 : nullptr, d_b16 ? d_b16 + (size_t)f0 * 256 : nullptr,

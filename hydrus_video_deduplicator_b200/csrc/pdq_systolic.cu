@@ -18,7 +18,6 @@
 #include <mutex>
 
 #include "common.cuh"
-#include "pdq_finalize.cuh"
 #include "pdq_systolic_core.h"
 
 namespace vpdq {
@@ -29,20 +28,12 @@ using namespace vpdq_sys;
 #endif
 constexpr int kSysWarps = VPDQS_WARPS;  // warps (= frames in flight) per SM: bounded by the raw rings in shared memory
 constexpr int kSysThreads = 32 * kSysWarps;
-constexpr int kFinThreads = 256;     // the finalize warps of the fused kernel (pdq_finalize.cuh is written for 256 threads)
-constexpr int kProducerRegs = 216;   // setmaxnreg: 8 x 32 x 216 + 8 x 32 x 40 = 65536 = the SM's register file
-constexpr int kConsumerRegs = 40;
 
 template <int CH>
 struct SysSmem {
     alignas(128) uint8_t ring[kSysWarps][Raw<CH>::kWarpRingBytes];
     alignas(128) uint8_t zeros[128];                    // the window of a stream row that is not an image row
     alignas(8) unsigned long long bar[kSysWarps][2];    // one mbarrier per in-flight event
-    // fused kernel only: the finalize warps' working set and the hand-over of finished planes
-    FinalizeSmem fin;
-    volatile int frames_done[kSysWarps];                // frames whose decimated plane is complete, per Jarosz warp
-    int frames_taken[kSysWarps];                        // ... and how many of them the finalize warps have taken
-    volatile long long pick;                            // the frame the finalize warps work on next (-1: give up)
 };
 
 __device__ int g_systolic_timeout = 0;  // set if an mbarrier wait gave up (never expected); read by the host at its sync points
@@ -97,84 +88,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-// frame range of Jarosz warp `warp` of CTA `cta`: warp index interleaved over the CTAs (a small batch spreads over the
-// SMs first), balanced split with the extra frames on the lowest warp indices
-__device__ __forceinline__ void warp_frames(long long n_frames_total, int warp, int cta, int n_ctas, long long& f_begin,
-                                            int& F) {
-    const long long wi = (long long)warp * n_ctas + cta, n_warps = (long long)kSysWarps * n_ctas;
-    const long long base = n_frames_total / n_warps, rem = n_frames_total % n_warps;
-    f_begin = wi * base + (wi < rem ? wi : rem);
-    F = (int)(base + (wi < rem ? 1 : 0));
-}
-
-// The finalize warps of the fused kernel (threads 256..511): take finished planes in the order they appear and turn
-// them into quality + hash with the same device function as k5_finalize.  They run in the issue slots and on the
-// shared-memory bandwidth the Jarosz warps leave idle.
-template <int CH>
-__device__ __forceinline__ void finalize_warps_main(SysSmem<CH>& sm, long long n_frames_total, const float* __restrict__ a64,
-                                                    const float* __restrict__ dct, uint8_t* __restrict__ hashes,
-                                                    int32_t* __restrict__ quality) {
-    const int c = threadIdx.x - kSysThreads;
-    auto sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kFinThreads) : "memory"); };
-    finalize_load_tables(sm.fin, dct, c);
-    long long total = 0;
-    for (int w = 0; w < kSysWarps; ++w) {
-        long long fb;
-        int F;
-        warp_frames(n_frames_total, w, blockIdx.x, gridDim.x, fb, F);
-        total += F;
-    }
-    sync();
-    int next_w = 0;
-    for (long long n = 0; n < total; ++n) {
-        if (c == 0) {  // wait for a finished plane, oldest producer first (round robin)
-            long long frame = -1;
-            for (long long spin = 0; frame < 0 && spin < (1ll << 24); ++spin) {
-                for (int k = 0; k < kSysWarps; ++k) {
-                    const int w = (next_w + k) % kSysWarps;
-                    if (sm.frames_done[w] > sm.frames_taken[w]) {
-                        long long fb;
-                        int F;
-                        warp_frames(n_frames_total, w, blockIdx.x, gridDim.x, fb, F);
-                        frame = fb + sm.frames_taken[w]++;
-                        next_w = (w + 1) % kSysWarps;
-                        break;
-                    }
-                }
-                if (frame < 0) __nanosleep(200);
-            }
-            if (frame < 0) g_systolic_timeout = 2;  // a Jarosz warp never delivered (never expected): fail loudly
-            sm.pick = frame;
-        }
-        sync();
-        const long long frame = sm.pick;
-        if (frame < 0) return;
-        __threadfence();  // acquire: the plane was written by other warps of this SM
-        finalize_frame(sm.fin, a64 + (size_t)frame * 4096, hashes + (size_t)frame * 32, quality + frame, nullptr, nullptr, c, sync);
-        sync();  // the shared buffers (and sm.pick) are reused by the next frame
-    }
-}
-
-// FUSE = false: kx_systolic_jarosz proper -- 8 warps, frames -> decimated planes a64.
-// FUSE = true : the whole PDQ hash in one persistent kernel -- the same 8 Jarosz warps (producers) plus 8 finalize warps
-//               (consumers, pdq_finalize.cuh) that pick every plane up as soon as it is complete; the register file is
-//               re-split with setmaxnreg (216 per Jarosz thread, 40 per finalize thread).
-template <int CH, bool FUSE>  // CH 3: RGB24 frames, 1: 8-bit gray frames (== R = G = B)
-__global__ void __launch_bounds__(FUSE ? kSysThreads + kFinThreads : kSysThreads, 1)
+template <int CH>  // 3: RGB24 frames, 1: 8-bit gray frames (== R = G = B)
+__global__ void __launch_bounds__(kSysThreads, 1)
     kx_systolic_jarosz(const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, int use3d,
-                       long long n_frames_total, float* __restrict__ a64, const float* __restrict__ dct,
-                       uint8_t* __restrict__ hashes, int32_t* __restrict__ quality) {
+                       long long n_frames_total, float* __restrict__ a64) {
     using R = Raw<CH>;
     extern __shared__ __align__(128) uint8_t smem_sys[];
     SysSmem<CH>& sm = *reinterpret_cast<SysSmem<CH>*>(smem_sys);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(sm.zeros)[threadIdx.x] = 0u;
-    if (threadIdx.x < kSysWarps) {
-        sm.frames_done[threadIdx.x] = 0;
-        sm.frames_taken[threadIdx.x] = 0;
-    }
-    if (warp < kSysWarps && lane == 0) {
+    if (lane == 0) {
         mbar_init(smem_u32(&sm.bar[warp][0]), 1);
         mbar_init(smem_u32(&sm.bar[warp][1]), 1);
     }
@@ -182,18 +106,12 @@ __global__ void __launch_bounds__(FUSE ? kSysThreads + kFinThreads : kSysThreads
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    if (FUSE) {
-        if (warp >= kSysWarps) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
-            finalize_warps_main<CH>(sm, n_frames_total, a64, dct, hashes, quality);
-            return;
-        }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-    }
-
-    long long f_begin;
-    int F;
-    warp_frames(n_frames_total, warp, blockIdx.x, gridDim.x, f_begin, F);
+    // warp index interleaved over the CTAs: a small batch spreads over the SMs first
+    const long long wi = (long long)warp * gridDim.x + blockIdx.x, n_warps = (long long)kSysWarps * gridDim.x;
+    // balanced split, the extra frames on the lowest warp indices (= spread over the CTAs)
+    const long long base = n_frames_total / n_warps, rem = n_frames_total % n_warps;
+    const long long f_begin = wi * base + (wi < rem ? wi : rem);
+    const int F = (int)(base + (wi < rem ? 1 : 0));
     if (F == 0) return;
     const int first_row = (int)(f_begin * 512);
 
@@ -258,8 +176,6 @@ __global__ void __launch_bounds__(FUSE ? kSysThreads + kFinThreads : kSysThreads
     L.init(lane);
     // stream position of lane 0 TWO steps ahead (lane 31 prepares that row's prologue pixels one luma stage early)
     int f0n = -1, r0n = kStepsPerFrame + kFirstStep + 2;
-    // stream position of lane 31 in THIS step (fused kernel: it emits the last decimated row of a frame at row 513)
-    int f31 = -1, r31 = kStepsPerFrame + kFirstStep - 31;
 
     for (int E = 0; E < first_loop_event(); ++E) issue_split(E);
     int issued = first_loop_event() - 1, waited = -1;
@@ -314,17 +230,6 @@ __global__ void __launch_bounds__(FUSE ? kSysThreads + kFinThreads : kSysThreads
         if (++r0n == kStepsPerFrame) {
             r0n = 0;
             ++f0n;
-        }
-        if (FUSE) {
-            if (r31 == kImageRows + 1 && (unsigned)f31 < (unsigned)F) {  // the plane of frame f31 is complete
-                __threadfence();  // every lane: its stores of this plane before ...
-                __syncwarp();
-                if (lane == 0) sm.frames_done[warp] = f31 + 1;  // ... the finalize warps may take it
-            }
-            if (++r31 == kStepsPerFrame) {
-                r31 = 0;
-                ++f31;
-            }
         }
     };
 
@@ -429,11 +334,8 @@ static int systolic_make_tensor_map(const uint8_t* d_frames, int64_t n_frames, i
     return VPDQ_B200_OK;
 }
 
-// RGB24 (channels = 3) or 8-bit gray (channels = 1) frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma
-// plane; with d_hashes != nullptr the fused kernel: the finalize warps turn every plane into hash + quality as well
-// (d_dct = the device copy of the DCT table).
-static int systolic_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, const float* d_dct,
-                           uint8_t* d_hashes, int32_t* d_quality, cudaStream_t stream) {
+// RGB24 (channels = 3) or 8-bit gray (channels = 1) frames -> a64 [n][64][64]: the Jarosz-filtered, decimated luma plane
+int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream) {
     if (n_frames > (int64_t)(0x7fffffff / 512) - 8) {
         set_error("pdq: at most %d frames per launch", 0x7fffffff / 512 - 8);
         return VPDQ_B200_ERR_INVALID;
@@ -456,48 +358,22 @@ static int systolic_launch(const uint8_t* d_frames, int channels, int64_t n_fram
     {
         std::lock_guard<std::mutex> lk(mu);
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            VPDQ_CUDA(cudaFuncSetAttribute(kx_systolic_jarosz<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            VPDQ_CUDA(cudaFuncSetAttribute(kx_systolic_jarosz<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(SysSmem<3>)));
-            VPDQ_CUDA(cudaFuncSetAttribute(kx_systolic_jarosz<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(SysSmem<1>)));
-            VPDQ_CUDA(cudaFuncSetAttribute(kx_systolic_jarosz<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(SysSmem<3>)));
-            VPDQ_CUDA(cudaFuncSetAttribute(kx_systolic_jarosz<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            VPDQ_CUDA(cudaFuncSetAttribute(kx_systolic_jarosz<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(SysSmem<1>)));
             if (dev >= 0 && dev < 64) attr_done[dev] = true;
         }
     }
     // persistent: one CTA per SM; fewer when the batch has fewer frames than the grid has warps
     const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);
-    const bool fuse = d_hashes != nullptr;
-    const unsigned threads = fuse ? kSysThreads + kFinThreads : kSysThreads;
-    if (channels == 3) {
-        if (fuse)
-            kx_systolic_jarosz<3, true><<<grid, threads, sizeof(SysSmem<3>), stream>>>(tmap, tmap3, use3d, (long long)n_frames,
-                                                                                        d_a64, d_dct, d_hashes, d_quality);
-        else
-            kx_systolic_jarosz<3, false><<<grid, threads, sizeof(SysSmem<3>), stream>>>(tmap, tmap3, use3d, (long long)n_frames,
-                                                                                         d_a64, nullptr, nullptr, nullptr);
-    } else {
-        if (fuse)
-            kx_systolic_jarosz<1, true><<<grid, threads, sizeof(SysSmem<1>), stream>>>(tmap, tmap3, use3d, (long long)n_frames,
-                                                                                        d_a64, d_dct, d_hashes, d_quality);
-        else
-            kx_systolic_jarosz<1, false><<<grid, threads, sizeof(SysSmem<1>), stream>>>(tmap, tmap3, use3d, (long long)n_frames,
-                                                                                         d_a64, nullptr, nullptr, nullptr);
-    }
+    if (channels == 3)
+        kx_systolic_jarosz<3><<<grid, kSysThreads, sizeof(SysSmem<3>), stream>>>(tmap, tmap3, use3d, (long long)n_frames, d_a64);
+    else
+        kx_systolic_jarosz<1><<<grid, kSysThreads, sizeof(SysSmem<1>), stream>>>(tmap, tmap3, use3d, (long long)n_frames, d_a64);
     g_launches += 1;
     VPDQ_CUDA(cudaGetLastError());
     return VPDQ_B200_OK;
-}
-
-int systolic_jarosz_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, cudaStream_t stream) {
-    return systolic_launch(d_frames, channels, n_frames, d_a64, nullptr, nullptr, nullptr, stream);
-}
-
-int systolic_pdq_launch(const uint8_t* d_frames, int channels, int64_t n_frames, float* d_a64, const float* d_dct,
-                        uint8_t* d_hashes, int32_t* d_quality, cudaStream_t stream) {
-    return systolic_launch(d_frames, channels, n_frames, d_a64, d_dct, d_hashes, d_quality, stream);
 }
 
 }  // namespace vpdq

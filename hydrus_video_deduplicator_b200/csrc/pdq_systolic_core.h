@@ -149,7 +149,7 @@ constexpr int kCols = 16;            // image columns per lane
 constexpr int kStepsPerFrame = 516;  // 512 image rows + 4 zero rows
 constexpr int kImageRows = 512;
 #ifndef VPDQS_RING_ROWS
-#define VPDQS_RING_ROWS 12
+#define VPDQS_RING_ROWS 16
 #endif
 constexpr int kRing = VPDQS_RING_ROWS;  // stream rows per group ring: 16 (4 box slots, 8 steps of TMA lead) or 12 (3, 4)
 constexpr int kBoxSlots = kRing / 4;
