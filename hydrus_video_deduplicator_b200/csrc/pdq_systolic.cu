@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     };
 
     auto step = [&](int t, auto jtag) {
-        constexpr int T8 = decltype(jtag)::value;
-        if ((T8 & 3) == kEventPhase) {
+        constexpr int T = decltype(jtag)::value;
+        // events every 4 steps: a compile-time position when the body is a multiple of 4, else a (uniform) test
+        if (kBody % 4 == 0 ? (T & 3) == kEventPhase : (t & 3) == kEventPhase) {
             const int Ew = (t + kWaitLead) >> 2, Ei = (t + kIssueLead) >> 2;
             if (Ew >= 0) {
                 wait(Ew);
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
             w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
         RowChain o1, o3;
-        lane_step<CH, T8>(L, w, lane, F, o1, o3, emit);
+        lane_step<CH, T>(L, w, lane, F, o1, o3, emit);
         const int src = (lane + 31) & 31;
         L.in1.s = __shfl_sync(0xffffffffu, o1.s, src);
         L.in1.h0 = __shfl_sync(0xffffffffu, o1.h0, src);
@@ -240,11 +241,11 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         step(t + 1, std::integral_constant<int, 1>{});
         step(t + 2, std::integral_constant<int, 2>{});
         step(t + 3, std::integral_constant<int, 3>{});
+        if (kBody >= 5) step(t + 4, std::integral_constant<int, 4 % kBody>{});
         if (kBody == 8) {
-            step(t + 4, std::integral_constant<int, 4>{});
-            step(t + 5, std::integral_constant<int, 5>{});
-            step(t + 6, std::integral_constant<int, 6>{});
-            step(t + 7, std::integral_constant<int, 7>{});
+            step(t + 5, std::integral_constant<int, 5 % kBody>{});
+            step(t + 6, std::integral_constant<int, 6 % kBody>{});
+            step(t + 7, std::integral_constant<int, 7 % kBody>{});
         }
     }
     for (int E = waited + 1; E <= issued; ++E) wait(E);  // no copy may be in flight when the CTA retires

@@ -159,8 +159,10 @@ constexpr int kGroups = 32 / kGroupLanes;  // 8
 #ifndef VPDQS_BODY
 #define VPDQS_BODY 4
 #endif
-constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4 or 8 (see LaneState)
-constexpr int kFirstStep = -8;       // the step loop starts here (a multiple of 8; steps < 0 only prepare lane 0's first row)
+constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4, 5 or 8 (see LaneState)
+constexpr int kHistSlots = kBody;    // slots of the 4-deep column-pass histories (> 4: the slot written differs from the one read)
+constexpr int kFirstStep = kBody == 5 ? -10 : -8;  // the step loop starts here (a multiple of kBody; steps < 0 only
+                                                   // prepare lane 0's first row)
 constexpr int kIssueLead = kRing - 6; // ISSUE(E) at step 4 E - 10 (ring of 16 rows; 4 E - 6 with 12): the earliest step at
                                      // which no lane still reads the box slot being refilled
 constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
@@ -224,7 +226,9 @@ VPDQS_HD bool event_is_one_box(int f, int r0, int n_frames) {
 // whose last output row 510 appears at row 512)
 VPDQS_HD int last_step(int F) { return kStepsPerFrame * (F - 1) + kImageRows + 1 + 31; }
 // events issued before the step loop starts
-VPDQS_HD int first_loop_event() { return (kFirstStep + kEventPhase + kIssueLead) / 4; }  // = 2
+VPDQS_HD int first_loop_event() {  // smallest E whose ISSUE step 4 E - kIssueLead falls inside the loop
+    return (kFirstStep + kIssueLead + 3 + 400) / 4 - 100;
+}
 
 struct RowChain {  // running sum over a row, window 4: s + the last four inputs (h0 oldest)
     float s, h0, h1, h2, h3;
@@ -237,20 +241,22 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
     return c.s;
 }
 
-// The step loop is unrolled by kBody: T8 = step & 7 selects the history slot (T8 & 3) and which of two register sets
-// a value is read from / written to, so that a new value is computed straight into its final register while the old
-// one is still being consumed (no register copies): the lumas alternate every step and, with kBody = 8, the
-// histories every 4 steps.  Measured on B200: the 8-step body saves 16 MOVs per step but its hot path (35 KB)
-// overflows the 32 KB L1.5 instruction cache ("no_instructions" stalls 3 % -> 19 %, 2 % slower overall), so the
-// product builds kBody = 4 (one history set; ptxas inserts the copies).
+// The step loop is unrolled by kBody and a step is compiled per position T in the body, so that every index below is
+// static.  The 4-deep histories of the column passes live in kHistSlots = kBody slots: the value fed at step u sits in
+// slot u mod kHistSlots, a step reads slot (u - 4) and writes slot u.  With 4 slots those are the same registers -- the
+// new value is produced while the old one is still needed, and ptxas has to park it and copy (16 MOVs per step);
+// with 5 or 8 slots it is computed straight into its final register.  Measured on B200: 8 slots (8-step body) save
+// the copies but the hot path (35 KB) overflows the 32 KB L1.5 instruction cache ("no_instructions" stalls 3 % ->
+// 19 %, 2 % slower overall); 5 slots (5-step body) keep the body small.
 struct LaneState {
     F2 s2[kCols / 2];         // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start
                               // of a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
                               // (one value for both: see the tail of lane_step for the divisor-3 rows)
-    F2 h2[kBody / 4][4][kCols / 2];   // P2 histories (the last four inputs): the value written at step u is h2[set(u)][u & 3]
-    F2 x[2][kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..) in x[step & 1], computed during the previous step
+    F2 h2[kHistSlots][kCols / 2];  // P2 histories (the last four inputs): the value fed at step u is h2[u mod kHistSlots]
+    F2 x[kBody % 2 == 0 ? 2 : 1][kCols / 2];  // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous
+                              // step; alternating sets x[step & 1] when the body is even
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
-    F2 h4[kBody / 4][4];
+    F2 h4[kHistSlots];
     RowChain in1, in3;        // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
     int r, f;                 // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
     // predicates that only change in the rare-row tail (so that the common path evaluates no row comparisons):
@@ -261,12 +267,12 @@ struct LaneState {
         for (int p = 0; p < kCols / 2; ++p) {
             s2[p] = f2_splat(0.0f);
             VPDQS_UNROLL
-            for (int j = 0; j < 4; ++j) h2[0][j][p] = h2[kBody / 4 - 1][j][p] = f2_splat(0.0f);
-            x[0][p] = x[1][p] = f2_splat(0.0f);
+            for (int j = 0; j < kHistSlots; ++j) h2[j][p] = f2_splat(0.0f);
+            x[0][p] = x[kBody % 2 == 0 ? 1 : 0][p] = f2_splat(0.0f);
         }
         s4 = f2_splat(0.0f);
         VPDQS_UNROLL
-        for (int j = 0; j < 4; ++j) h4[0][j] = h4[kBody / 4 - 1][j] = f2_splat(0.0f);
+        for (int j = 0; j < kHistSlots; ++j) h4[j] = f2_splat(0.0f);
         in1 = row_zero();
         in3 = row_zero();
         // stream row of lane l at the first step = kFirstStep - l < 0: rows of the virtual frame -1 (never live)
@@ -276,9 +282,8 @@ struct LaneState {
         zmask = 0u;
     }
 };
-// where the history value written at step u (u & 7 = U8) lives
-VPDQS_HD constexpr int hist_set(int U8) { return kBody == 8 ? ((((U8 + 8) & 7) >> 2) & 1) ^ 1 : 0; }
-VPDQS_HD constexpr int hist_slot(int U8) { return (U8 + 8) & 3; }
+// slot of the history value fed at body position U (U may be negative: earlier steps)
+VPDQS_HD constexpr int hist_slot(int U) { return ((U % kHistSlots) + kHistSlots) % kHistSlots; }
 
 // u8 -> fp32 product without an I2F: the byte is spliced into the mantissa of a power of two, M = 2^k + byte exactly, and
 // fma(c, M, -c * 2^k) = RN(c * byte) -- bit-identical to __fmul_rn(c, (float)byte) (c * 2^k is exact).  Bytes 2 and 3 of a
@@ -314,7 +319,7 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
     return f2_add(f2_add(r, g), b);  // (0.299 R + 0.587 G) + 0.114 B
 }
 
-// One lane, one step.  T8 = step & 7.  w = the raw window of the lane's NEXT stream row (zeros when that row is not an
+// One lane, one step.  T = position of the step in the loop body (step mod kBody).  w = the raw window of the lane's NEXT stream row (zeros when that row is not an
 // image row: L.img_next); for lane 31 the LAST chunk is instead the first 16 bytes of the row lane 0 works on TWO
 // steps ahead (zeros if that is not an image row).
 //
@@ -324,21 +329,22 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
 // into the tail for the rare rows (divisor-3 rows, the frame boundary).
 // out1 / out3: the chain states to hand to lane l + 1 (lane 31 -> lane 0: the next row's initial states).
 // emit(v0, v1): the next decimated row (in order: rows 0..63 of frame 0, 1, ...) of columns 2l, 2l+1 is final.
-template <int CH, int T8, typename Emit>
+template <int CH, int T, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
-    constexpr int J = T8 & 3, PX = T8 & 1, PH = kBody == 8 ? (T8 >> 2) & 1 : 0, PHW = kBody == 8 ? PH ^ 1 : 0;
+    constexpr int JW = hist_slot(T), JR = hist_slot(T - 4);            // history slot written / read by this step
+    constexpr int XR = kBody % 2 == 0 ? (T & 1) : 0, XW = kBody % 2 == 0 ? XR ^ 1 : 0;  // luma set read / written
     const int r = L.r;
     RowChain c1 = L.in1, c3 = L.in3;
     float z0 = 0.0f, z1 = 0.0f;
     const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u, first = lane == 0 ? 0xFFFFFFFFu : 0u;
     // lane 31: its last two lumas are the NEXT row's pixels 0, 1 (its own row has only the drain zeros left there)
-    const float xa = L.x[PX][7].x, xb = L.x[PX][7].y;
+    const float xa = L.x[XR][7].x, xb = L.x[XR][7].y;
     VPDQS_UNROLL
     for (int p = 0; p < kCols / 2; ++p) {
         const int k = 2 * p;
-        L.x[PX ^ 1][p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
-        F2 x = L.x[PX][p];
+        F2 x = L.x[XR][p];
+        L.x[XW][p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
         if (p == 7) x = F2{bitkeep(~last, x.x), bitkeep(~last, x.y)};
         // P1: row pass 1 along the lanes -> output columns 16 l + k, + 1 (unscaled, x4)
         float v0 = row_feed(c1, x.x);
@@ -347,10 +353,10 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         const float v1 = row_feed(c1, x.y);
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
-        const F2 old = L.h2[PH][J][p], prev = L.s2[p];
+        const F2 old = L.h2[JR][p], prev = L.s2[p];
         F2 s = f2_add(prev, v);
         s = f2_sub(s, old);
-        L.h2[PHW][J][p] = v;
+        L.h2[JW][p] = v;
         L.s2[p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
@@ -362,10 +368,10 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
     // P4: column pass 2, private, fed P3 row r - 3 (zeros unless real) -> output row r - 5
     {
         const F2 z{bitkeep(L.zmask, z0), bitkeep(L.zmask, z1)};
-        const F2 old = L.h4[PH][J];
+        const F2 old = L.h4[JR];
         F2 s = f2_add(L.s4, z);
         s = f2_sub(s, old);
-        L.h4[PHW][J] = z;
+        L.h4[JW] = z;
         L.s4 = s;
         if (L.zmask && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
             emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
@@ -396,10 +402,8 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         if (r == 3) {
             VPDQS_UNROLL
             for (int p = 0; p < kCols / 2; ++p)
-                L.s2[p] = f2_add(f2_add(f2_add(L.h2[hist_set(T8 - 3)][hist_slot(T8 - 3)][p],
-                                               L.h2[hist_set(T8 - 2)][hist_slot(T8 - 2)][p]),
-                                        L.h2[hist_set(T8 - 1)][hist_slot(T8 - 1)][p]),
-                                 L.h2[hist_set(T8)][hist_slot(T8)][p]);
+                L.s2[p] = f2_add(f2_add(f2_add(L.h2[hist_slot(T - 3)][p], L.h2[hist_slot(T - 2)][p]), L.h2[hist_slot(T - 1)][p]),
+                                 L.h2[hist_slot(T)][p]);
         }
         if (r == kImageRows - 2) L.img_next = false;     // the step after next reads row 512: not an image row
         if (r == kImageRows + 1) L.zmask = 0u;           // P2 output row 510 was the last real one

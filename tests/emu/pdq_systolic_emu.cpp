@@ -106,7 +106,7 @@ struct WarpSim {
     }
 };
 
-template <int CH, int T8>
+template <int CH, int T>
 void step_all(WarpSim<CH>& W, LaneState* st, float** optr, int t) {
     using R = Raw<CH>;
     RowChain out1[32], out3[32];
@@ -121,7 +121,7 @@ void step_all(WarpSim<CH>& W, LaneState* st, float** optr, int t) {
         if (st[lane].img_next)
             for (int q = 0; q < R::kChunks - (lane == 31 ? 1 : 0); ++q) W.read_chunk(lane, s, q, w + 4 * q);
         if (lane == 31 && next0_image) W.read_chunk(0, next0, 0, w + 4 * (R::kChunks - 1));
-        lane_step<CH, T8>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](float v0, float v1) {
+        lane_step<CH, T>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](float v0, float v1) {
             optr[lane][0] = v0;
             optr[lane][1] = v1;
             optr[lane] += 64;
@@ -164,15 +164,15 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 W->issue(Ei);
                 issued = Ei;
             }
-            switch (t & 7) {
+            switch (((t - kFirstStep) % kBody)) {  // position in the loop body (kFirstStep is a multiple of kBody)
                 case 0: step_all<CH, 0>(*W, st, optr, t); break;
                 case 1: step_all<CH, 1>(*W, st, optr, t); break;
                 case 2: step_all<CH, 2>(*W, st, optr, t); break;
                 case 3: step_all<CH, 3>(*W, st, optr, t); break;
-                case 4: step_all<CH, 4>(*W, st, optr, t); break;
-                case 5: step_all<CH, 5>(*W, st, optr, t); break;
-                case 6: step_all<CH, 6>(*W, st, optr, t); break;
-                default: step_all<CH, 7>(*W, st, optr, t); break;
+                case 4: step_all<CH, 4 % kBody>(*W, st, optr, t); break;
+                case 5: step_all<CH, 5 % kBody>(*W, st, optr, t); break;
+                case 6: step_all<CH, 6 % kBody>(*W, st, optr, t); break;
+                default: step_all<CH, 7 % kBody>(*W, st, optr, t); break;
             }
         }
         for (int E = waited + 1; E <= issued; ++E) W->wait(E);
