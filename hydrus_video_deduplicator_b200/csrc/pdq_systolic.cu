@@ -149,11 +149,11 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         __syncwarp();
         if (has) tma_load_2d(dst, &tmap2, box_x<CH>(lane), y, bar);
     };
-    // (f, r0) of group 0's box of the next event to issue in the loop; in the common case (all eight boxes inside one
-    // frame) the event is ONE 3-D box
-    int ev_f = 0, ev_r = kBoxRows * first_loop_event();
+    // an event in the general form: ONE 3-D box when all eight group boxes lie inside one live frame, else per group
     auto issue = [&](int E) {
-        if (use3d && event_is_one_box(ev_f, ev_r, F)) {
+        const int s00 = box_first_row(E, 0);
+        const int ev_f = s00 >= 0 ? s00 / kStepsPerFrame : -1, ev_r = s00 - ev_f * kStepsPerFrame;
+        if (use3d && s00 >= 0 && event_is_one_box(ev_f, ev_r, F)) {
             if (lane == 0) {
                 const uint32_t bar = bar0 + 8 * (E & 1);
                 mbar_expect_tx(bar, kGroups * R::kBoxBytes);
@@ -164,18 +164,11 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         } else {
             issue_split(E);
         }
-        ev_r += kBoxRows;
-        if (ev_r == kStepsPerFrame) {
-            ev_r = 0;
-            ++ev_f;
-        }
     };
     auto wait = [&](int E) { mbar_wait(bar0 + 8 * (E & 1), (uint32_t)((E >> 1) & 1)); };
 
     LaneState L;
     L.init(lane);
-    // stream position of lane 0 TWO steps ahead (lane 31 prepares that row's prologue pixels one luma stage early)
-    int f0n = -1, r0n = kStepsPerFrame + kFirstStep + 2;
 
     for (int E = 0; E < first_loop_event(); ++E) issue_split(E);
     int issued = first_loop_event() - 1, waited = -1;
@@ -186,25 +179,43 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         optr += 64;
     };
 
-    auto step = [&](int t, auto jtag) {
+    // stream position of lane 0 at the first step of the iteration (uniform)
+    int f0 = -1, r0 = kStepsPerFrame + kFirstStep;
+
+    // One step.  PLAIN (pdq_systolic_core.h, iteration_is_plain): every window is staged, the event is one 3-D box.
+    auto step = [&](int t, auto jtag, auto ptag) {
         constexpr int T = decltype(jtag)::value;
+        constexpr bool PLAIN = decltype(ptag)::value;
         // events every 4 steps: a compile-time position when the body is a multiple of 4, else a (uniform) test
-        if (kBody % 4 == 0 ? (T & 3) == kEventPhase : (t & 3) == kEventPhase) {
+        // (an even body keeps the parity of t: no test at all in the odd positions)
+        if (kBody % 4 == 0 ? (T & 3) == kEventPhase : (kBody % 2 != 0 || T % 2 == kEventPhase % 2) && (t & 3) == kEventPhase) {
             const int Ew = (t + kWaitLead) >> 2, Ei = (t + kIssueLead) >> 2;
-            if (Ew >= 0) {
+            if (PLAIN || Ew >= 0) {
                 wait(Ew);
                 waited = Ew;
             }
-            issue(Ei);
+            if (PLAIN) {
+                if (lane == 0) {
+                    const uint32_t bar = bar0 + 8 * (Ei & 1);
+                    mbar_expect_tx(bar, kGroups * R::kBoxBytes);
+                    tma_load_3d(ring + (Ei % kBoxSlots) * (kGroups * R::kBoxBytes), &tmap3, 0,
+                                first_row + f0 * 512 + plain_event_row(r0) - View3<CH>::kBackRows, 0, bar);
+                }
+                __syncwarp();
+            } else {
+                issue(Ei);
+            }
             issued = Ei;
         }
         // the raw window of the NEXT step's row (its lumas are this step's filler work)
         uint32_t w[R::kWords];
         {
             const int a = t + lane_a;
-            const uint32_t off = L.img_next ? lane_base + ((a >> 2) % kBoxSlots) * (kGroups * R::kBoxBytes) + (a & 3) * R::kSegPitch : zeros;
-            const bool nimg = (unsigned)f0n < (unsigned)F && r0n < kImageRows;
-            const uint32_t last31 = nimg ? grp0_base + ring_row_offset<CH>(0, t + 2) : zeros;
+            const uint32_t win = lane_base + ((a >> 2) % kBoxSlots) * (kGroups * R::kBoxBytes) + (a & 3) * R::kSegPitch;
+            const uint32_t off = PLAIN || L.img_next ? win : zeros;
+            const int s2 = t + 2;  // the stream row of lane 0 two steps ahead (lane 31 prepares its prologue pixels)
+            const bool nimg = PLAIN || (s2 >= 0 && s2 / kStepsPerFrame < F && s2 % kStepsPerFrame < kImageRows);
+            const uint32_t last31 = nimg ? grp0_base + ring_row_offset<CH>(0, s2) : zeros;
             const uint32_t last = lane == 31 ? last31 : off + 16 * (R::kChunks - 1);
 #pragma unroll
             for (int q = 0; q < R::kChunks - 1; ++q) {
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
             w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
         RowChain o1, o3;
-        lane_step<CH, T>(L, w, lane, F, o1, o3, emit);
+        lane_step<CH, T, PLAIN>(L, w, lane, F, o1, o3, emit);
         const int src = (lane + 31) & 31;
         L.in1.s = __shfl_sync(0xffffffffu, o1.s, src);
         L.in1.h0 = __shfl_sync(0xffffffffu, o1.h0, src);
@@ -228,24 +239,31 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         L.in3.h1 = __shfl_sync(0xffffffffu, o3.h1, src);
         L.in3.h2 = __shfl_sync(0xffffffffu, o3.h2, src);
         L.in3.h3 = __shfl_sync(0xffffffffu, o3.h3, src);
-        if (++r0n == kStepsPerFrame) {
-            r0n = 0;
-            ++f0n;
+    };
+    auto body = [&](int t, auto ptag) {
+        step(t, std::integral_constant<int, 0>{}, ptag);
+        step(t + 1, std::integral_constant<int, 1>{}, ptag);
+        step(t + 2, std::integral_constant<int, 2>{}, ptag);
+        step(t + 3, std::integral_constant<int, 3>{}, ptag);
+        if (kBody >= 5) step(t + 4, std::integral_constant<int, 4 % kBody>{}, ptag);
+        if (kBody >= 6) step(t + 5, std::integral_constant<int, 5 % kBody>{}, ptag);
+        if (kBody == 8) {
+            step(t + 6, std::integral_constant<int, 6 % kBody>{}, ptag);
+            step(t + 7, std::integral_constant<int, 7 % kBody>{}, ptag);
         }
     };
 
     const int t_last = last_step(F);
 #pragma unroll 1
     for (int t = kFirstStep; t <= t_last; t += kBody) {  // (steps past t_last only see rows that are not live)
-        step(t, std::integral_constant<int, 0>{});
-        step(t + 1, std::integral_constant<int, 1>{});
-        step(t + 2, std::integral_constant<int, 2>{});
-        step(t + 3, std::integral_constant<int, 3>{});
-        if (kBody >= 5) step(t + 4, std::integral_constant<int, 4 % kBody>{});
-        if (kBody == 8) {
-            step(t + 5, std::integral_constant<int, 5 % kBody>{});
-            step(t + 6, std::integral_constant<int, 6 % kBody>{});
-            step(t + 7, std::integral_constant<int, 7 % kBody>{});
+        if (use3d && iteration_is_plain(f0, r0, F))
+            body(t, std::true_type{});
+        else
+            body(t, std::false_type{});
+        r0 += kBody;
+        if (r0 >= kStepsPerFrame) {
+            r0 -= kStepsPerFrame;
+            ++f0;
         }
     }
     for (int E = waited + 1; E <= issued; ++E) wait(E);  // no copy may be in flight when the CTA retires

@@ -159,10 +159,10 @@ constexpr int kGroups = 32 / kGroupLanes;  // 8
 #ifndef VPDQS_BODY
 #define VPDQS_BODY 4
 #endif
-constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4, 5 or 8 (see LaneState)
+constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4, 5, 6 or 8 (see LaneState)
 constexpr int kHistSlots = kBody;    // slots of the 4-deep column-pass histories (> 4: the slot written differs from the one read)
-constexpr int kFirstStep = kBody == 5 ? -10 : -8;  // the step loop starts here (a multiple of kBody; steps < 0 only
-                                                   // prepare lane 0's first row)
+constexpr int kFirstStep = -((8 + kBody - 1) / kBody) * kBody;  // the step loop starts here (a multiple of kBody <= -8;
+                                                                // steps < 0 only prepare lane 0's first row)
 constexpr int kIssueLead = kRing - 6; // ISSUE(E) at step 4 E - 10 (ring of 16 rows; 4 E - 6 with 12): the earliest step at
                                      // which no lane still reads the box slot being refilled
 constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
@@ -230,6 +230,20 @@ VPDQS_HD int first_loop_event() {  // smallest E whose ISSUE step 4 E - kIssueLe
     return (kFirstStep + kIssueLead + 3 + 400) / 4 - 100;
 }
 
+// The step loop has TWO bodies.  An iteration (kBody steps from step t0, lane 0 on stream row r0 of frame f0, both
+// uniform) is PLAIN when during all of its steps every lane is on a row 4 <= r <= 509 of a live frame: no divisor-3
+// row, no frame boundary, every window staged, P4 fed a real row -- and its TMA event is one 3-D box.  Plain
+// iterations (90 % of a frame) run lane_step<.., true>: one basic block per kBody steps, no per-lane row tests at
+// all.  The others run the general lane_step<.., false>, which tracks (r, f) per lane and branches into the tail for
+// the rare rows.
+VPDQS_HD constexpr int plain_event_row(int r0) { return r0 + ((kEventPhase + kIssueLead) & ~3); }  // group 0's first row of
+                                                                                                // the event issued in the iteration
+VPDQS_HD bool iteration_is_plain(int f0, int r0, int n_frames) {
+    return kBody == 4 && (unsigned)f0 < (unsigned)n_frames && r0 >= 4 + 31 && r0 + kBody - 1 <= kImageRows - 3 &&
+           r0 + kBody - 1 + 2 < kImageRows &&                                   // lane 31's view of lane 0's row two steps ahead
+           plain_event_row(r0) <= kImageRows - kBoxRows;                          // (>= 28 follows from r0 >= 35)
+}
+
 struct RowChain {  // running sum over a row, window 4: s + the last four inputs (h0 oldest)
     float s, h0, h1, h2, h3;
 };
@@ -258,7 +272,8 @@ struct LaneState {
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
     F2 h4[kHistSlots];
     RowChain in1, in3;        // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
-    int r, f;                 // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame)
+    int r, f;                 // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame).
+                              // Plain iterations only advance r, once, after their last step
     // predicates that only change in the rare-row tail (so that the common path evaluates no row comparisons):
     bool img_next;            // the NEXT step's row is an image row of one of the warp's frames (its window is staged)
     uint32_t zmask;           // all ones iff this step's P3 row (P2 output row r - 3) is real: 3 <= r <= 513 of a live frame
@@ -329,12 +344,13 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
 // into the tail for the rare rows (divisor-3 rows, the frame boundary).
 // out1 / out3: the chain states to hand to lane l + 1 (lane 31 -> lane 0: the next row's initial states).
 // emit(v0, v1): the next decimated row (in order: rows 0..63 of frame 0, 1, ...) of columns 2l, 2l+1 is final.
-template <int CH, int T, typename Emit>
+// PLAIN: the step belongs to a plain iteration (iteration_is_plain): L.r is the row of the iteration's FIRST step.
+template <int CH, int T, bool PLAIN, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
     constexpr int JW = hist_slot(T), JR = hist_slot(T - 4);            // history slot written / read by this step
     constexpr int XR = kBody % 2 == 0 ? (T & 1) : 0, XW = kBody % 2 == 0 ? XR ^ 1 : 0;  // luma set read / written
-    const int r = L.r;
+    const int r = PLAIN ? L.r + T : L.r;
     RowChain c1 = L.in1, c3 = L.in3;
     float z0 = 0.0f, z1 = 0.0f;
     const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u, first = lane == 0 ? 0xFFFFFFFFu : 0u;
@@ -367,13 +383,13 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
     }
     // P4: column pass 2, private, fed P3 row r - 3 (zeros unless real) -> output row r - 5
     {
-        const F2 z{bitkeep(L.zmask, z0), bitkeep(L.zmask, z1)};
+        const F2 z = PLAIN ? F2{z0, z1} : F2{bitkeep(L.zmask, z0), bitkeep(L.zmask, z1)};
         const F2 old = L.h4[JR];
         F2 s = f2_add(L.s4, z);
         s = f2_sub(s, old);
         L.h4[JW] = z;
         L.s4 = s;
-        if (L.zmask && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
+        if ((PLAIN || L.zmask) && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
             emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
     }
     // hand-over (lane 31 -> lane 0, next row: the chain after the prologue pixels 0, 1, fed without output / a fresh chain)
@@ -381,6 +397,10 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
                     bitsel(last, xb, c1.h3)};
     out3 = RowChain{bitkeep(~last, c3.s), bitkeep(~last, c3.h0), bitkeep(~last, c3.h1), bitkeep(~last, c3.h2),
                     bitkeep(~last, c3.h3)};
+    if (PLAIN) {
+        if (T == kBody - 1) L.r += kBody;
+        return;
+    }
     L.r = r + 1;
     // ---- tail: the rare rows ----
     if (VPDQS_UNLIKELY((unsigned)(r - 2) < 2u || r >= kImageRows - 2)) {

@@ -106,7 +106,7 @@ struct WarpSim {
     }
 };
 
-template <int CH, int T>
+template <int CH, int T, bool PLAIN>
 void step_all(WarpSim<CH>& W, LaneState* st, float** optr, int t) {
     using R = Raw<CH>;
     RowChain out1[32], out3[32];
@@ -118,10 +118,16 @@ void step_all(WarpSim<CH>& W, LaneState* st, float** optr, int t) {
         const int s = t + 1 - lane;  // the NEXT step's row of this lane
         const bool want = s >= 0 && s / kStepsPerFrame < W.F && s % kStepsPerFrame < kImageRows;
         if (want != st[lane].img_next) ++W.errors;  // the loop-carried predicate must agree with the stream position
+        if (PLAIN) {  // what a plain iteration takes for granted, per lane
+            const int row = t - lane;
+            if (!want || !next0_image || st[lane].zmask != 0xFFFFFFFFu || row < 0 || st[lane].r + T != row % kStepsPerFrame ||
+                st[lane].f != row / kStepsPerFrame || row % kStepsPerFrame < 4 || row % kStepsPerFrame > kImageRows - 3)
+                ++W.errors;
+        }
         if (st[lane].img_next)
             for (int q = 0; q < R::kChunks - (lane == 31 ? 1 : 0); ++q) W.read_chunk(lane, s, q, w + 4 * q);
         if (lane == 31 && next0_image) W.read_chunk(0, next0, 0, w + 4 * (R::kChunks - 1));
-        lane_step<CH, T>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](float v0, float v1) {
+        lane_step<CH, T, PLAIN>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](float v0, float v1) {
             optr[lane][0] = v0;
             optr[lane][1] = v1;
             optr[lane] += 64;
@@ -157,24 +163,52 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
         for (int E = 0; E < first_loop_event(); ++E) W->issue(E);
         int issued = first_loop_event() - 1, waited = -1;
         const int t_last = last_step(F);
-        for (int t = kFirstStep; t <= t_last; ++t) {
+        int f0 = -1, r0 = kStepsPerFrame + kFirstStep;  // lane 0's stream position at the first step of the iteration
+        bool plain = false;
+        int plain_iterations = 0, iterations = 0;
+        for (int t = kFirstStep; t <= t_last || (t - kFirstStep) % kBody != 0; ++t) {  // (the kernel finishes its last body)
+            const int T = (t - kFirstStep) % kBody;  // position in the loop body (kFirstStep is a multiple of kBody)
+            if (T == 0) {
+                plain = iteration_is_plain(f0, r0, F);
+                plain_iterations += plain;
+                ++iterations;
+            }
             if ((t & 3) == kEventPhase) {
                 const int Ew = (t + kWaitLead) / 4, Ei = (t + kIssueLead) / 4;
                 if (Ew >= 0) { W->wait(Ew); waited = Ew; }
-                W->issue(Ei);
+                if (plain) {  // the kernel issues the 3-D box at row plain_event_row(r0) of frame f0 without looking
+                    const int s00 = box_first_row(Ei, 0), before = W->one_box_events;
+                    if (Ew < 0 || s00 != f0 * kStepsPerFrame + plain_event_row(r0)) ++W->errors;
+                    W->issue(Ei);
+                    if (W->one_box_events != before + 1) ++W->errors;
+                } else {
+                    W->issue(Ei);
+                }
                 issued = Ei;
             }
-            switch (((t - kFirstStep) % kBody)) {  // position in the loop body (kFirstStep is a multiple of kBody)
-                case 0: step_all<CH, 0>(*W, st, optr, t); break;
-                case 1: step_all<CH, 1>(*W, st, optr, t); break;
-                case 2: step_all<CH, 2>(*W, st, optr, t); break;
-                case 3: step_all<CH, 3>(*W, st, optr, t); break;
-                case 4: step_all<CH, 4 % kBody>(*W, st, optr, t); break;
-                case 5: step_all<CH, 5 % kBody>(*W, st, optr, t); break;
-                case 6: step_all<CH, 6 % kBody>(*W, st, optr, t); break;
-                default: step_all<CH, 7 % kBody>(*W, st, optr, t); break;
+            switch (T + (plain ? 8 : 0)) {
+                case 0: step_all<CH, 0, false>(*W, st, optr, t); break;
+                case 1: step_all<CH, 1, false>(*W, st, optr, t); break;
+                case 2: step_all<CH, 2, false>(*W, st, optr, t); break;
+                case 3: step_all<CH, 3, false>(*W, st, optr, t); break;
+                case 4: step_all<CH, 4 % kBody, false>(*W, st, optr, t); break;
+                case 5: step_all<CH, 5 % kBody, false>(*W, st, optr, t); break;
+                case 6: step_all<CH, 6 % kBody, false>(*W, st, optr, t); break;
+                case 7: step_all<CH, 7 % kBody, false>(*W, st, optr, t); break;
+                case 8: step_all<CH, 0, true>(*W, st, optr, t); break;
+                case 9: step_all<CH, 1, true>(*W, st, optr, t); break;
+                case 10: step_all<CH, 2, true>(*W, st, optr, t); break;
+                default: step_all<CH, 3, true>(*W, st, optr, t); break;  // (plain iterations exist for kBody == 4 only)
+            }
+            if (T == kBody - 1) {
+                r0 += kBody;
+                if (r0 >= kStepsPerFrame) {
+                    r0 -= kStepsPerFrame;
+                    ++f0;
+                }
             }
         }
+        if (kBody == 4 && F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
         for (int E = waited + 1; E <= issued; ++E) W->wait(E);
         if (!W->pending.empty()) ++errors;
         for (int l = 0; l < 32; ++l)
