@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
 
     // stream position of lane 0 at the first step of the iteration (uniform)
     int f0 = -1, r0 = kStepsPerFrame + kFirstStep;
+    int plain_y = 0;  // see the plain run below
 
     // One step.  PLAIN (pdq_systolic_core.h, iteration_is_plain): every window is staged, the event is one 3-D box.
     auto step = [&](int t, auto jtag, auto ptag) {
@@ -198,8 +199,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
                 if (lane == 0) {
                     const uint32_t bar = bar0 + 8 * (Ei & 1);
                     mbar_expect_tx(bar, kGroups * R::kBoxBytes);
-                    tma_load_3d(ring + (Ei % kBoxSlots) * (kGroups * R::kBoxBytes), &tmap3, 0,
-                                first_row + f0 * 512 + plain_event_row(r0) - View3<CH>::kBackRows, 0, bar);
+                    tma_load_3d(ring + (Ei % kBoxSlots) * (kGroups * R::kBoxBytes), &tmap3, 0, plain_y + t, 0, bar);
                 }
                 __syncwarp();
             } else {
@@ -254,16 +254,26 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     };
 
     const int t_last = last_step(F);
+    int t = kFirstStep;
 #pragma unroll 1
-    for (int t = kFirstStep; t <= t_last; t += kBody) {  // (steps past t_last only see rows that are not live)
-        if (use3d && iteration_is_plain(f0, r0, F))
-            body(t, std::true_type{});
-        else
+    while (t <= t_last) {  // (steps past t_last only see rows that are not live)
+        if (use3d && iteration_is_plain(f0, r0, F)) {
+            // a run of plain iterations: its own loop, so that its registers are allocated on their own.  The event
+            // issued at step t (T == kEventPhase) is the 3-D box at global row
+            //   first_row + 512 f0 + plain_event_row(r0) - 28,  r0 = (t - kEventPhase) - 516 f0   ==   plain_y + t
+            const int n = plain_run_length(r0);
+            plain_y = first_row - (kStepsPerFrame - 512) * f0 + plain_event_row(-kEventPhase) - View3<CH>::kBackRows;
+#pragma unroll 1
+            for (int k = 0; k < n; ++k, t += kBody) body(t, std::true_type{});
+            r0 += kBody * n;
+        } else {
             body(t, std::false_type{});
-        r0 += kBody;
-        if (r0 >= kStepsPerFrame) {
-            r0 -= kStepsPerFrame;
-            ++f0;
+            t += kBody;
+            r0 += kBody;
+            if (r0 >= kStepsPerFrame) {
+                r0 -= kStepsPerFrame;
+                ++f0;
+            }
         }
     }
     for (int E = waited + 1; E <= issued; ++E) wait(E);  // no copy may be in flight when the CTA retires

@@ -238,11 +238,16 @@ VPDQS_HD int first_loop_event() {  // smallest E whose ISSUE step 4 E - kIssueLe
 // the rare rows.
 VPDQS_HD constexpr int plain_event_row(int r0) { return r0 + ((kEventPhase + kIssueLead) & ~3); }  // group 0's first row of
                                                                                                 // the event issued in the iteration
+constexpr int kPlainFirst = (4 + 31 + 3) & ~3;  // 36: lane 31 is on row >= 4 (r0 is a multiple of 4: 516 = 4 * 129)
+constexpr int kPlainLastA = kImageRows - 3 - (kBody - 1);                         // lane 0 stays on rows <= 509 (and lane 31
+                                                                                  // sees an image row two steps ahead of it)
+constexpr int kPlainLastB = kImageRows - kBoxRows - ((kEventPhase + kIssueLead) & ~3);  // the event's last group-0 row is <= 511
+constexpr int kPlainLast = (kPlainLastA < kPlainLastB ? kPlainLastA : kPlainLastB) & ~3;  // 496 (ring of 16 rows)
 VPDQS_HD bool iteration_is_plain(int f0, int r0, int n_frames) {
-    return kBody == 4 && (unsigned)f0 < (unsigned)n_frames && r0 >= 4 + 31 && r0 + kBody - 1 <= kImageRows - 3 &&
-           r0 + kBody - 1 + 2 < kImageRows &&                                   // lane 31's view of lane 0's row two steps ahead
-           plain_event_row(r0) <= kImageRows - kBoxRows;                          // (>= 28 follows from r0 >= 35)
+    return kBody == 4 && (unsigned)f0 < (unsigned)n_frames && r0 >= kPlainFirst && r0 <= kPlainLast;
 }
+// consecutive plain iterations from r0 on (the kernel runs them as one inner loop)
+VPDQS_HD int plain_run_length(int r0) { return (kPlainLast - r0) / kBody + 1; }
 
 struct RowChain {  // running sum over a row, window 4: s + the last four inputs (h0 oldest)
     float s, h0, h1, h2, h3;
