@@ -157,7 +157,7 @@ constexpr int kBoxRows = 4;          // stream rows per TMA box
 constexpr int kGroupLanes = 4;
 constexpr int kGroups = 32 / kGroupLanes;  // 8
 #ifndef VPDQS_BODY
-#define VPDQS_BODY 4
+#define VPDQS_BODY 8
 #endif
 constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4, 5, 6 or 8 (see LaneState)
 constexpr int kHistSlots = kBody;    // slots of the 4-deep column-pass histories (> 4: the slot written differs from the one read)
@@ -238,13 +238,13 @@ VPDQS_HD int first_loop_event() {  // smallest E whose ISSUE step 4 E - kIssueLe
 // the rare rows.
 VPDQS_HD constexpr int plain_event_row(int r0) { return r0 + ((kEventPhase + kIssueLead) & ~3); }  // group 0's first row of
                                                                                                 // the event issued in the iteration
-constexpr int kPlainFirst = (4 + 31 + 3) & ~3;  // 36: lane 31 is on row >= 4 (r0 is a multiple of 4: 516 = 4 * 129)
-constexpr int kPlainLastA = kImageRows - 3 - (kBody - 1);                         // lane 0 stays on rows <= 509 (and lane 31
-                                                                                  // sees an image row two steps ahead of it)
-constexpr int kPlainLastB = kImageRows - kBoxRows - ((kEventPhase + kIssueLead) & ~3);  // the event's last group-0 row is <= 511
-constexpr int kPlainLast = (kPlainLastA < kPlainLastB ? kPlainLastA : kPlainLastB) & ~3;  // 496 (ring of 16 rows)
+constexpr int kPlainFirst = 4 + 31;  // lane 31 is on row >= 4 (r0 itself is a multiple of 4: 516 = 4 * 129)
+constexpr int kPlainLastA = kImageRows - 3 - (kBody - 1);  // lane 0 stays on rows <= 509 (and lane 31 sees an image row two
+                                                           // steps ahead of it)
+constexpr int kPlainLastB = kImageRows - kBoxRows - plain_event_row(kBody - 4);  // the LAST event's group-0 rows are <= 511
+constexpr int kPlainLast = kPlainLastA < kPlainLastB ? kPlainLastA : kPlainLastB;  // 496 (body of 4 steps, ring of 16 rows)
 VPDQS_HD bool iteration_is_plain(int f0, int r0, int n_frames) {
-    return kBody == 4 && (unsigned)f0 < (unsigned)n_frames && r0 >= kPlainFirst && r0 <= kPlainLast;
+    return kBody % 4 == 0 && (unsigned)f0 < (unsigned)n_frames && r0 >= kPlainFirst && r0 <= kPlainLast;
 }
 // consecutive plain iterations from r0 on (the kernel runs them as one inner loop)
 VPDQS_HD int plain_run_length(int r0) { return (kPlainLast - r0) / kBody + 1; }

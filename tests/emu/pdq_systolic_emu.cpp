@@ -178,7 +178,7 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 if (Ew >= 0) { W->wait(Ew); waited = Ew; }
                 if (plain) {  // the kernel issues the 3-D box at row plain_event_row(r0) of frame f0 without looking
                     const int s00 = box_first_row(Ei, 0), before = W->one_box_events;
-                    if (Ew < 0 || s00 != f0 * kStepsPerFrame + plain_event_row(r0)) ++W->errors;
+                    if (Ew < 0 || s00 != f0 * kStepsPerFrame + plain_event_row(r0 + T - kEventPhase)) ++W->errors;
                     W->issue(Ei);
                     if (W->one_box_events != before + 1) ++W->errors;
                 } else {
@@ -198,7 +198,11 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 case 8: step_all<CH, 0, true>(*W, st, optr, t); break;
                 case 9: step_all<CH, 1, true>(*W, st, optr, t); break;
                 case 10: step_all<CH, 2, true>(*W, st, optr, t); break;
-                default: step_all<CH, 3, true>(*W, st, optr, t); break;  // (plain iterations exist for kBody == 4 only)
+                case 11: step_all<CH, 3, true>(*W, st, optr, t); break;
+                case 12: step_all<CH, 4 % kBody, true>(*W, st, optr, t); break;  // (plain iterations: kBody 4 or 8)
+                case 13: step_all<CH, 5 % kBody, true>(*W, st, optr, t); break;
+                case 14: step_all<CH, 6 % kBody, true>(*W, st, optr, t); break;
+                default: step_all<CH, 7 % kBody, true>(*W, st, optr, t); break;
             }
             if (T == kBody - 1) {
                 r0 += kBody;
@@ -208,7 +212,7 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 }
             }
         }
-        if (kBody == 4 && F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
+        if (kBody % 4 == 0 && F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
         for (int E = waited + 1; E <= issued; ++E) W->wait(E);
         if (!W->pending.empty()) ++errors;
         for (int l = 0; l < 32; ++l)
