@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
             if (lane == 0) {
                 const uint32_t bar = bar0 + 8 * (E & 1);
                 mbar_expect_tx(bar, kGroups * R::kBoxBytes);
-                tma_load_3d(ring + (E % kBoxSlots) * (kGroups * R::kBoxBytes), &tmap3, 0,
+                tma_load_3d(ring + box_slot_of(E) * (kGroups * R::kBoxBytes), &tmap3, 0,
                             first_row + ev_f * 512 + ev_r - View3<CH>::kBackRows, 0, bar);
             }
             __syncwarp();
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
                 if (lane == 0) {
                     const uint32_t bar = bar0 + 8 * (Ei & 1);
                     mbar_expect_tx(bar, kGroups * R::kBoxBytes);
-                    tma_load_3d(ring + (Ei % kBoxSlots) * (kGroups * R::kBoxBytes), &tmap3, 0, plain_y + t, 0, bar);
+                    tma_load_3d(ring + box_slot_of(Ei) * (kGroups * R::kBoxBytes), &tmap3, 0, plain_y + t, 0, bar);
                 }
                 __syncwarp();
             } else {
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         uint32_t w[R::kWords];
         {
             const int a = t + lane_a;
-            const uint32_t win = lane_base + ((a >> 2) % kBoxSlots) * (kGroups * R::kBoxBytes) + (a & 3) * R::kSegPitch;
+            const uint32_t win = lane_base + box_slot_of(a >> 2) * (kGroups * R::kBoxBytes) + (a & 3) * R::kSegPitch;
             const uint32_t off = PLAIN || L.img_next ? win : zeros;
             const int s2 = t + 2;  // the stream row of lane 0 two steps ahead (lane 31 prepares its prologue pixels)
             const bool nimg = PLAIN || (s2 >= 0 && s2 / kStepsPerFrame < F && s2 % kStepsPerFrame < kImageRows);

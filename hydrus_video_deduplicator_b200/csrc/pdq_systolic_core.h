@@ -153,6 +153,11 @@ constexpr int kImageRows = 512;
 #endif
 constexpr int kRing = VPDQS_RING_ROWS;  // stream rows per group ring: 16 (4 box slots, 8 steps of TMA lead) or 12 (3, 4)
 constexpr int kBoxSlots = kRing / 4;
+// box slot of ring row index a (= stream row + 4 * group): floor-mod; a mask when the slot count is a power of two (a may
+// be negative in the first steps, where the result is not used)
+VPDQS_HD constexpr int box_slot_of(int a4) {
+    return (kBoxSlots & (kBoxSlots - 1)) == 0 ? (a4 & (kBoxSlots - 1)) : ((a4 % kBoxSlots) + kBoxSlots) % kBoxSlots;
+}
 constexpr int kBoxRows = 4;          // stream rows per TMA box
 constexpr int kGroupLanes = 4;
 constexpr int kGroups = 32 / kGroupLanes;  // 8
@@ -195,7 +200,7 @@ VPDQS_HD int ring_group_offset(int g) { return (kGroups - 1 - g) * Raw<CH>::kBox
 template <int CH>
 VPDQS_HD int ring_row_offset(int g, int s) {
     const int a = s + kGroupLanes * g;
-    return ((a >> 2) % kBoxSlots) * (kGroups * Raw<CH>::kBoxBytes) + (a & 3) * Raw<CH>::kSegPitch;
+    return box_slot_of(a >> 2) * (kGroups * Raw<CH>::kBoxBytes) + (a & 3) * Raw<CH>::kSegPitch;
 }
 // byte offset (inside the warp's ring) of the window of `lane` for stream row s
 template <int CH>
@@ -205,7 +210,7 @@ VPDQS_HD int ring_offset(int lane, int s) {
 // the TMA box of event E for group g: first stream row (may be negative = nothing to load)
 VPDQS_HD int box_first_row(int E, int g) { return kBoxRows * E - kGroupLanes * g; }
 template <int CH>
-VPDQS_HD int box_ring_offset(int g, int E) { return (E % kBoxSlots) * (kGroups * Raw<CH>::kBoxBytes) + ring_group_offset<CH>(g); }
+VPDQS_HD int box_ring_offset(int g, int E) { return box_slot_of(E) * (kGroups * Raw<CH>::kBoxBytes) + ring_group_offset<CH>(g); }
 template <int CH>
 VPDQS_HD int box_x(int g) { return g * Raw<CH>::kSegBytes; }
 // The 3-D view of the batch that makes all 8 boxes of an event one TMA box: element (x, y, g') lives at byte
@@ -274,6 +279,8 @@ struct LaneState {
     F2 h2[kHistSlots][kCols / 2];  // P2 histories (the last four inputs): the value fed at step u is h2[u mod kHistSlots]
     F2 x[kBody % 2 == 0 ? 2 : 1][kCols / 2];  // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous
                               // step; alternating sets x[step & 1] when the body is even
+    F2 keep;                  // plain 8-step iterations: the decimated pair of this iteration (every lane has exactly one: its
+                              // rows advance by 8), stored once after the last step
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
     F2 h4[kHistSlots];
     RowChain in1, in3;        // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
@@ -290,7 +297,7 @@ struct LaneState {
             for (int j = 0; j < kHistSlots; ++j) h2[j][p] = f2_splat(0.0f);
             x[0][p] = x[kBody % 2 == 0 ? 1 : 0][p] = f2_splat(0.0f);
         }
-        s4 = f2_splat(0.0f);
+        s4 = keep = f2_splat(0.0f);
         VPDQS_UNROLL
         for (int j = 0; j < kHistSlots; ++j) h4[j] = f2_splat(0.0f);
         in1 = row_zero();
@@ -394,8 +401,14 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         s = f2_sub(s, old);
         L.h4[JW] = z;
         L.s4 = s;
-        if ((PLAIN || L.zmask) && (r & 7) == 1)  // output row r - 5 = 8 i + 4, r = 9, 17, .., 513
+        // output row r - 5 = 8 i + 4 at r = 9, 17, .., 513
+        if (PLAIN && kBody == 8) {
+            const uint32_t m = (r & 7) == 1 ? 0xFFFFFFFFu : 0u;
+            L.keep = T == 0 ? s : F2{bitsel(m, s.x, L.keep.x), bitsel(m, s.y, L.keep.y)};  // (T == 0: any value will do)
+            if (T == kBody - 1) emit(fmul(L.keep.x, 0.00390625f), fmul(L.keep.y, 0.00390625f));
+        } else if ((PLAIN || L.zmask) && (r & 7) == 1) {
             emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
+        }
     }
     // hand-over (lane 31 -> lane 0, next row: the chain after the prologue pixels 0, 1, fed without output / a fresh chain)
     out1 = RowChain{bitsel(last, fadd(xa, xb), c1.s), bitkeep(~last, c1.h0), bitkeep(~last, c1.h1), bitsel(last, xa, c1.h2),

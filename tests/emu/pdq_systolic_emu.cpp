@@ -34,7 +34,7 @@ struct WarpSim {
     int errors = 0;
     int one_box_events = 0, split_events = 0;
 
-    static int row_index(int g, int s) { return (((s + kGroupLanes * g) >> 2) % kBoxSlots) * 4 + (s & 3); }
+    static int row_index(int g, int s) { return box_slot_of((s + kGroupLanes * g) >> 2) * 4 + (s & 3); }
     void invalidate(int g, int s0) {
         for (int i = 0; i < kBoxRows; ++i) slot_row[g][row_index(g, s0 + i)] = -2000000000;
     }
