@@ -212,9 +212,11 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         {
             const int a = t + lane_a;
             const uint32_t win = lane_base + box_slot_of(a >> 2) * (kGroups * R::kBoxBytes) + (a & 3) * R::kSegPitch;
-            const uint32_t off = PLAIN || L.img_next ? win : zeros;
+            const uint32_t off = PLAIN || L.img_next(F) ? win : zeros;
             const int s2 = t + 2;  // the stream row of lane 0 two steps ahead (lane 31 prepares its prologue pixels)
-            const bool nimg = PLAIN || (s2 >= 0 && s2 / kStepsPerFrame < F && s2 % kStepsPerFrame < kImageRows);
+            const int rr = r0 + T + 2 >= kStepsPerFrame ? r0 + T + 2 - kStepsPerFrame : r0 + T + 2;
+            const int ff = r0 + T + 2 >= kStepsPerFrame ? f0 + 1 : f0;
+            const bool nimg = PLAIN || (rr < kImageRows && (unsigned)ff < (unsigned)F);
             const uint32_t last31 = nimg ? grp0_base + ring_row_offset<CH>(0, s2) : zeros;
             const uint32_t last = lane == 31 ? last31 : off + 16 * (R::kChunks - 1);
 #pragma unroll

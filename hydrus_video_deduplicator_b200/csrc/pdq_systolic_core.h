@@ -136,13 +136,20 @@ VPDQS_HD float div3(float v) {
     const float r = ffma(-3.0f, q, v);
     return ffma(r, c, q);
 }
-// a divisor-3 output in the deferred-scale representation
-VPDQS_HD float edge3(float v) { return fmul(div3(v), 4.0f); }
+// a divisor-3 output in the deferred-scale representation: 4 * RN(v / 3) = RN(4 v / 3), the same Markstein sequence run
+// on 4 v with the power of two folded into the constants (q = v * 4c, r / 4 = v - 0.75 q, q + (r / 4) * 4c) -- three
+// operations, bit-identical to fmul(div3(v), 4) for every normal float (tests/emu/div3_check.c)
+VPDQS_HD float edge3(float v) {
+    const float c4 = 1.33333337306976318f;  // 0x3FAAAAAB = 4 * 0x3EAAAAAB
+    const float q = fmul(v, c4);
+    const float r = ffma(-0.75f, q, v);
+    return ffma(r, c4, q);
+}
 VPDQS_HD F2 edge3(F2 v) {  // the same on a packed pair (no multiply feeds an add here: nothing for ptxas to contract)
-    const F2 c = f2_splat(0.333333343267440796f);
-    const F2 q = f2_mul(v, c);
-    const F2 r = f2_fma(f2_splat(-3.0f), q, v);
-    return f2_mul(f2_fma(r, c, q), f2_splat(4.0f));
+    const F2 c4 = f2_splat(1.33333337306976318f);
+    const F2 q = f2_mul(v, c4);
+    const F2 r = f2_fma(f2_splat(-0.75f), q, v);
+    return f2_fma(r, c4, q);
 }
 
 constexpr int kCols = 16;            // image columns per lane
@@ -279,16 +286,18 @@ struct LaneState {
     F2 h2[kHistSlots][kCols / 2];  // P2 histories (the last four inputs): the value fed at step u is h2[u mod kHistSlots]
     F2 x[kBody % 2 == 0 ? 2 : 1][kCols / 2];  // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous
                               // step; alternating sets x[step & 1] when the body is even
-    F2 keep;                  // plain 8-step iterations: the decimated pair of this iteration (every lane has exactly one: its
-                              // rows advance by 8), stored once after the last step
+    F2 keep;                  // the decimated pair a lane produces during an iteration of 8 steps (exactly one in a plain
+    bool have;                // iteration: its rows advance by 8; at most one otherwise), stored once after the last step
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
     F2 h4[kHistSlots];
     RowChain in1, in3;        // chain states handed over by lane l - 1 for THIS step (P1: row r; P3: P2-row r - 3)
     int r, f;                 // stream position of this step: row 0 .. 515 of frame f (relative to the warp's first frame).
                               // Plain iterations only advance r, once, after their last step
-    // predicates that only change in the rare-row tail (so that the common path evaluates no row comparisons):
-    bool img_next;            // the NEXT step's row is an image row of one of the warp's frames (its window is staged)
-    uint32_t zmask;           // all ones iff this step's P3 row (P2 output row r - 3) is real: 3 <= r <= 513 of a live frame
+    // the NEXT step's row is an image row of one of the warp's frames (its window is staged; else the lane reads zeros)
+    VPDQS_HD bool img_next(int n_frames) const {
+        return (r <= kImageRows - 2 && (unsigned)f < (unsigned)n_frames) ||
+               (r == kStepsPerFrame - 1 && (unsigned)(f + 1) < (unsigned)n_frames);
+    }
     VPDQS_HD void init(int lane) {
         VPDQS_UNROLL
         for (int p = 0; p < kCols / 2; ++p) {
@@ -305,8 +314,7 @@ struct LaneState {
         // stream row of lane l at the first step = kFirstStep - l < 0: rows of the virtual frame -1 (never live)
         f = -1;
         r = kStepsPerFrame + kFirstStep - lane;
-        img_next = false;
-        zmask = 0u;
+        have = false;
     }
 };
 // slot of the history value fed at body position U (U may be negative: earlier steps)
@@ -346,23 +354,35 @@ VPDQS_HD F2 luma_pair_at(const uint32_t (&w)[N], int b0) {
     return f2_add(f2_add(r, g), b);  // (0.299 R + 0.587 G) + 0.114 B
 }
 
-// One lane, one step.  T = position of the step in the loop body (step mod kBody).  w = the raw window of the lane's NEXT stream row (zeros when that row is not an
-// image row: L.img_next); for lane 31 the LAST chunk is instead the first 16 bytes of the row lane 0 works on TWO
-// steps ahead (zeros if that is not an image row).
+// One lane, one step.  T = position of the step in the loop body (step mod kBody).  w = the raw window of the lane's
+// NEXT stream row (zeros when that row is not an image row: L.img_next()); for lane 31 the LAST chunk is instead the
+// first 16 bytes of the row lane 0 works on TWO steps ahead (zeros if that is not an image row).
 //
-// The step is one branch-free main block in which the two serial chains -- P1 over this step's row r and P3 over
-// the P2 outputs of the PREVIOUS step (output row r - 3) -- start with every input ready and run side by side with
-// the independent work (P2, and the lumas of the NEXT step's row) that fills their latency, followed by ONE branch
-// into the tail for the rare rows (divisor-3 rows, the frame boundary).
+// The step is ONE branch-free block in which the two serial chains -- P1 over this step's row r and P3 over the P2
+// outputs of the PREVIOUS step (output row r - 3) -- start with every input ready and run side by side with the
+// independent work (P2, and the lumas of the NEXT step's row) that fills their latency.
+// PLAIN: the step belongs to a plain iteration (iteration_is_plain): every lane is on a row 4 <= r <= 509 of a live
+// frame and L.r is the row of the iteration's FIRST step.  Otherwise the rare rows are handled per lane -- still
+// without a branch, by what the row number selects:
+//   r == 0            the P2 sums restart (they hold rounding residue after the four zero rows): the sum's first
+//                     operation is fma(prev, 0, v) instead of fma(prev, 1, v) == prev + v
+//   r == 3, r == 513  P3 is fed P2 output rows 0 / 510, whose divisor is 3: edge3(prev) instead of prev (the P2 sums
+//                     themselves stay untouched and keep running)
+//   r == 3            the P4 sums restart the same way (their histories were flushed by five zero feeds)
+//   r < 3, r > 513, or a frame that is not live: P4 is fed zeros and nothing is emitted
 // out1 / out3: the chain states to hand to lane l + 1 (lane 31 -> lane 0: the next row's initial states).
 // emit(v0, v1): the next decimated row (in order: rows 0..63 of frame 0, 1, ...) of columns 2l, 2l+1 is final.
-// PLAIN: the step belongs to a plain iteration (iteration_is_plain): L.r is the row of the iteration's FIRST step.
 template <int CH, int T, bool PLAIN, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
     constexpr int JW = hist_slot(T), JR = hist_slot(T - 4);            // history slot written / read by this step
     constexpr int XR = kBody % 2 == 0 ? (T & 1) : 0, XW = kBody % 2 == 0 ? XR ^ 1 : 0;  // luma set read / written
     const int r = PLAIN ? L.r + T : L.r;
+    const bool live = PLAIN || (unsigned)L.f < (unsigned)n_frames;
+    const bool edge_row = !PLAIN && (r == 3 || r == kImageRows + 1);
+    const bool fed = PLAIN || (live && r >= 3 && r <= kImageRows + 1);   // this step's P3 row is a real P2 output row
+    const float keep2 = (PLAIN || r != 0) ? 1.0f : 0.0f, keep4 = (PLAIN || r != 3) ? 1.0f : 0.0f;
+    const uint32_t fedmask = fed ? 0xFFFFFFFFu : 0u;
     RowChain c1 = L.in1, c3 = L.in3;
     float z0 = 0.0f, z1 = 0.0f;
     const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u, first = lane == 0 ? 0xFFFFFFFFu : 0u;
@@ -382,32 +402,39 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
         const F2 old = L.h2[JR][p], prev = L.s2[p];
-        F2 s = f2_add(prev, v);
+        F2 s = PLAIN ? f2_add(prev, v) : f2_fma(prev, f2_splat(keep2), v);  // (prev * 1 + v == prev + v, one rounding)
         s = f2_sub(s, old);
         L.h2[JW][p] = v;
         L.s2[p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
-        const float u0 = row_feed(c3, prev.x);
+        F2 pin = prev;
+        if (!PLAIN) {
+            const F2 e = edge3(prev);
+            if (edge_row) pin = e;
+        }
+        const float u0 = row_feed(c3, pin.x);
         if (k == 6) z0 = u0;
         if (k == 14) z1 = u0;
-        row_feed(c3, prev.y);
+        row_feed(c3, pin.y);
     }
     // P4: column pass 2, private, fed P3 row r - 3 (zeros unless real) -> output row r - 5
     {
-        const F2 z = PLAIN ? F2{z0, z1} : F2{bitkeep(L.zmask, z0), bitkeep(L.zmask, z1)};
+        const F2 z = PLAIN ? F2{z0, z1} : F2{bitkeep(fedmask, z0), bitkeep(fedmask, z1)};
         const F2 old = L.h4[JR];
-        F2 s = f2_add(L.s4, z);
+        F2 s = PLAIN ? f2_add(L.s4, z) : f2_fma(L.s4, f2_splat(keep4), z);
         s = f2_sub(s, old);
         L.h4[JW] = z;
         L.s4 = s;
         // output row r - 5 = 8 i + 4 at r = 9, 17, .., 513
-        if (PLAIN && kBody == 8) {
-            const uint32_t m = (r & 7) == 1 ? 0xFFFFFFFFu : 0u;
+        const bool now = fed && (r & 7) == 1;
+        if (kBody == 8) {  // one store per lane and iteration: a lane meets at most one such row in 8 steps
+            const uint32_t m = now ? 0xFFFFFFFFu : 0u;
             L.keep = T == 0 ? s : F2{bitsel(m, s.x, L.keep.x), bitsel(m, s.y, L.keep.y)};  // (T == 0: any value will do)
-            if (T == kBody - 1) emit(fmul(L.keep.x, 0.00390625f), fmul(L.keep.y, 0.00390625f));
-        } else if ((PLAIN || L.zmask) && (r & 7) == 1) {
-            emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));  // the deferred 4^-4
+            L.have = PLAIN ? true : (T == 0 ? now : (L.have || now));
+            if (T == kBody - 1 && L.have) emit(fmul(L.keep.x, 0.00390625f), fmul(L.keep.y, 0.00390625f));  // the deferred 4^-4
+        } else if (now) {
+            emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));
         }
     }
     // hand-over (lane 31 -> lane 0, next row: the chain after the prologue pixels 0, 1, fed without output / a fresh chain)
@@ -417,41 +444,10 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
                     bitkeep(~last, c3.h3)};
     if (PLAIN) {
         if (T == kBody - 1) L.r += kBody;
-        return;
-    }
-    L.r = r + 1;
-    // ---- tail: the rare rows ----
-    if (VPDQS_UNLIKELY((unsigned)(r - 2) < 2u || r >= kImageRows - 2)) {
-        const bool live = (unsigned)L.f < (unsigned)n_frames;
-        // P2 output rows 0 (r = 2) and 510 (r = 512) have divisor 3.  The sums double as P3's input of the next step,
-        // so the fix-up is done IN PLACE (no second set of registers, no copies in the common path): after row 510
-        // the sums are dead anyway (zero rows follow, reset at the frame start); after row 0 the next step's P2
-        // update runs on the fixed-up value and is wrong for this lane -- its tail (r = 3) rebuilds the sums from the
-        // history, which at that point holds exactly rows 0..3: ((v0 + v1) + v2) + v3, the very operations of the
-        // running sum (its subtractions are all of zeros there).
-        if (r == 2 || r == kImageRows) {
-            VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = edge3(L.s2[p]);
-        }
-        if (r == 2) {  // P4 is first fed a real row in the next step (r = 3); its histories were flushed by 5 zero feeds
-            L.s4 = f2_splat(0.0f);
-            L.zmask = live ? 0xFFFFFFFFu : 0u;
-        }
-        if (r == 3) {
-            VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p)
-                L.s2[p] = f2_add(f2_add(f2_add(L.h2[hist_slot(T - 3)][p], L.h2[hist_slot(T - 2)][p]), L.h2[hist_slot(T - 1)][p]),
-                                 L.h2[hist_slot(T)][p]);
-        }
-        if (r == kImageRows - 2) L.img_next = false;     // the step after next reads row 512: not an image row
-        if (r == kImageRows + 1) L.zmask = 0u;           // P2 output row 510 was the last real one
-        if (r == kStepsPerFrame - 2) L.img_next = (unsigned)(L.f + 1) < (unsigned)n_frames;  // row 0 of the next frame
-        if (r == kStepsPerFrame - 1) {  // next step starts a new frame: the P2 histories were flushed by the four zero
-            L.r = 0;                    // rows, the sums hold rounding residue
-            ++L.f;
-            VPDQS_UNROLL
-            for (int p = 0; p < kCols / 2; ++p) L.s2[p] = f2_splat(0.0f);
-        }
+    } else {
+        const bool wrap = r == kStepsPerFrame - 1;
+        L.r = wrap ? 0 : r + 1;
+        L.f += wrap ? 1 : 0;
     }
 }
 

@@ -117,14 +117,14 @@ void step_all(WarpSim<CH>& W, LaneState* st, float** optr, int t) {
         memset(w, 0, sizeof w);
         const int s = t + 1 - lane;  // the NEXT step's row of this lane
         const bool want = s >= 0 && s / kStepsPerFrame < W.F && s % kStepsPerFrame < kImageRows;
-        if (want != st[lane].img_next) ++W.errors;  // the loop-carried predicate must agree with the stream position
+        if (want != st[lane].img_next(W.F)) ++W.errors;  // the lane's own view must agree with the stream position
         if (PLAIN) {  // what a plain iteration takes for granted, per lane
             const int row = t - lane;
-            if (!want || !next0_image || st[lane].zmask != 0xFFFFFFFFu || row < 0 || st[lane].r + T != row % kStepsPerFrame ||
+            if (!want || !next0_image || row < 0 || st[lane].r + T != row % kStepsPerFrame ||
                 st[lane].f != row / kStepsPerFrame || row % kStepsPerFrame < 4 || row % kStepsPerFrame > kImageRows - 3)
                 ++W.errors;
         }
-        if (st[lane].img_next)
+        if (st[lane].img_next(W.F))
             for (int q = 0; q < R::kChunks - (lane == 31 ? 1 : 0); ++q) W.read_chunk(lane, s, q, w + 4 * q);
         if (lane == 31 && next0_image) W.read_chunk(0, next0, 0, w + 4 * (R::kChunks - 1));
         lane_step<CH, T, PLAIN>(st[lane], w, lane, W.F, out1[lane], out3[lane], [&](float v0, float v1) {
