@@ -145,11 +145,13 @@ VPDQS_HD float edge3(float v) {
     const float r = ffma(-0.75f, q, v);
     return ffma(r, c4, q);
 }
-VPDQS_HD F2 edge3(F2 v) {  // the same on a packed pair (no multiply feeds an add here: nothing for ptxas to contract)
-    const F2 c4 = f2_splat(1.33333337306976318f);
-    const F2 q = f2_mul(v, c4);
-    const F2 r = f2_fma(f2_splat(-0.75f), q, v);
-    return f2_fma(r, c4, q);
+constexpr float kEdge3C = 1.33333337306976318f;
+// the same on a packed pair, with the constants as arguments: (kEdge3C, -0.75) -> edge3(v); (1, -1) -> v itself, exactly
+// (no multiply feeds an add here: nothing for ptxas to contract)
+VPDQS_HD F2 edge3_if(F2 v, float c, float k) {
+    const F2 q = f2_mul(v, f2_splat(c));
+    const F2 r = f2_fma(f2_splat(k), q, v);
+    return f2_fma(r, f2_splat(kEdge3C), q);
 }
 
 constexpr int kCols = 16;            // image columns per lane
@@ -383,6 +385,7 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
     const bool fed = PLAIN || (live && r >= 3 && r <= kImageRows + 1);   // this step's P3 row is a real P2 output row
     const float keep2 = (PLAIN || r != 0) ? 1.0f : 0.0f, keep4 = (PLAIN || r != 3) ? 1.0f : 0.0f;
     const uint32_t fedmask = fed ? 0xFFFFFFFFu : 0u;
+    const float edge_c = edge_row ? kEdge3C : 1.0f, edge_k = edge_row ? -0.75f : -1.0f;
     RowChain c1 = L.in1, c3 = L.in3;
     float z0 = 0.0f, z1 = 0.0f;
     const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u, first = lane == 0 ? 0xFFFFFFFFu : 0u;
@@ -408,11 +411,9 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         L.s2[p] = s;
         // P3: row pass 2 along the lanes over the previous step's P2 outputs -> output column 16 l + k - 2; only the
         // decimated columns 8 j + 4 are kept
-        F2 pin = prev;
-        if (!PLAIN) {
-            const F2 e = edge3(prev);
-            if (edge_row) pin = e;
-        }
+        // (rare rows: edge3 with its two constants switched to 1 on every other row, which makes it the identity --
+        // q = prev * 1, the residual prev - 1 * q = +0, q + 0 * c = prev -- without a select per value)
+        const F2 pin = PLAIN ? prev : edge3_if(prev, edge_c, edge_k);
         const float u0 = row_feed(c3, pin.x);
         if (k == 6) z0 = u0;
         if (k == 14) z1 = u0;
