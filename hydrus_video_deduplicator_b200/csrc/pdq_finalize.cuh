@@ -123,22 +123,42 @@ __device__ __forceinline__ void finalize_frame(FinalizeSmem& sm, const float* __
             acc = fadd(acc, fmul(tv.w, dv.w));
         }
         bv = acc;
-        sm.B[t] = acc;
     }
-    sync();
     if (b16_dbg) b16_dbg[t] = bv;
 
     // median = 128-th smallest of the 256 values (what Torben's method returns for n = 256) = the largest value v
-    // with #{B < v} <= 127.  Keys: an order-preserving map float -> int (of v + 0.0f, so that -0 == +0).
+    // with #{B < v} <= 127.  #{B < v} per thread without the 256 x 256 comparisons: every warp sorts its 32 values
+    // (bitonic network over shuffles) and publishes the list; a thread then counts, per list, the values below its
+    // own with a branch-free lower bound -- the list in the warp's registers, probed with index shuffles.
+    // Keys: an order-preserving map float -> int (of v + 0.0f, so that -0 == +0).
     int key = __float_as_int(fadd(bv, 0.0f));
     key ^= (key >> 31) & 0x7fffffff;
     {
+        const int lane = t & 31;
+        float sv = bv;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j >= 1; j >>= 1) {
+                const float o = __shfl_xor_sync(0xffffffffu, sv, j);
+                const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+                sv = take_min ? fminf(sv, o) : fmaxf(sv, o);
+            }
+        }
+        sm.B[t] = sv;  // [warp][rank in the warp]
+        sync();
         int lt = 0;
-        const float4* b4 = reinterpret_cast<const float4*>(sm.B);
-#pragma unroll 16
-        for (int u = 0; u < 64; ++u) {
-            const float4 b = b4[u];
-            lt += (b.x < bv) + (b.y < bv) + (b.z < bv) + (b.w < bv);
+#pragma unroll
+        for (int wl = 0; wl < 8; ++wl) {
+            const float lv = sm.B[32 * wl + lane];
+            int pos = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const float e = __shfl_sync(0xffffffffu, lv, pos + step - 1);
+                pos += e < bv ? step : 0;
+            }
+            const float e = __shfl_sync(0xffffffffu, lv, pos);
+            lt += pos + (e < bv ? 1 : 0);
         }
         const int cand = __reduce_max_sync(0xffffffffu, lt <= 127 ? key : INT_MIN);
         if ((t & 31) == 0) atomicMax(&sm.med_key, cand);
