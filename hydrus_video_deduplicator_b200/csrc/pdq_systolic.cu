@@ -187,9 +187,8 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     auto step = [&](int t, auto jtag, auto ptag) {
         constexpr int T = decltype(jtag)::value;
         constexpr bool PLAIN = decltype(ptag)::value;
-        // events every 4 steps: a compile-time position when the body is a multiple of 4, else a (uniform) test
-        // (an even body keeps the parity of t: no test at all in the odd positions)
-        if (kBody % 4 == 0 ? (T & 3) == kEventPhase : (kBody % 2 != 0 || T % 2 == kEventPhase % 2) && (t & 3) == kEventPhase) {
+        // events every 4 steps, at a compile-time position in the body
+        if ((T & 3) == kEventPhase) {
             const int Ew = (t + kWaitLead) >> 2, Ei = (t + kIssueLead) >> 2;
             if (PLAIN || Ew >= 0) {
                 wait(Ew);
@@ -247,9 +246,9 @@ __global__ void __launch_bounds__(kSysThreads, 1)
         step(t + 1, std::integral_constant<int, 1>{}, ptag);
         step(t + 2, std::integral_constant<int, 2>{}, ptag);
         step(t + 3, std::integral_constant<int, 3>{}, ptag);
-        if (kBody >= 5) step(t + 4, std::integral_constant<int, 4 % kBody>{}, ptag);
-        if (kBody >= 6) step(t + 5, std::integral_constant<int, 5 % kBody>{}, ptag);
         if (kBody == 8) {
+            step(t + 4, std::integral_constant<int, 4 % kBody>{}, ptag);
+            step(t + 5, std::integral_constant<int, 5 % kBody>{}, ptag);
             step(t + 6, std::integral_constant<int, 6 % kBody>{}, ptag);
             step(t + 7, std::integral_constant<int, 7 % kBody>{}, ptag);
         }

@@ -4,7 +4,7 @@
 //
 // Why.  The Jarosz filter is a running sum (s += x[r]; s -= x[l]; y = s / n), so every output carries the
 // rounding history of its whole line prefix and each line is an inherently serial fp32 chain.
-// The tiled kernels (pdq_fused*.cu) gave every lane whole lines and therefore had to transpose the plane
+// The round-1 tiled kernels (tests/legacy/pdq_fused*.cu) gave every lane whole lines and therefore had to transpose the plane
 // through shared memory between the row and the column passes: 4 tile crossings + 2 raw crossings, 5.6 MB per
 // frame through a 128 B/clk pipe -- the measured bound of those kernels ("What's weak" 2).
 // Here the data never moves; the CHAIN STATE does:
@@ -31,13 +31,17 @@
 //     aligned with what it feeds into P3, whose decimated outputs 8 j + 4 (j = 2 l, 2 l + 1) appear at k = 6, 14.
 //     The row prologue (pixels 0, 1 fed without output) is computed by lane 31 one step ahead in the two slots
 //     where its own row has only zeros left, and rides the rotate-shuffle into lane 0.
-//   * column chains: feeding row r yields output row r - 2; history slot = step & 3 (static after unrolling
-//     the step loop by 4).  P2 outputs rows 0 and 510 (divisor 3) are fixed up at r = 2 and r = 512.  P3 and P4
-//     run ONE STEP BEHIND P2 (so that the two serial row chains of a step, P1 of row r and P3 of P2-row r - 3,
-//     are independent and interleave in one basic block): P4 is fed P3 rows r - 3 for 3 <= r <= 513 (zeros
-//     otherwise) and emits decimated row i at r = 8 i + 9.
-//   * deferred power-of-two scaling as in pdq_fused2_core.h: planes stay unscaled (x4 per pass), divisor-3
-//     outputs become 4 * div3(s), the single multiply by 2^-8 happens on the 4096 emitted values.
+//   * column chains: feeding row r yields output row r - 2; history slot = step & 7 (static after unrolling
+//     the step loop by 8).  P2 output rows 0 and 510 have divisor 3: the lane applies it to what it feeds into P3
+//     (at r = 3 and r = 513), the running sums themselves are never touched.  P3 and P4 run ONE STEP BEHIND P2 (so
+//     that the two serial row chains of a step, P1 of row r and P3 of P2-row r - 3, are independent and interleave
+//     in one basic block): P4 is fed P3 rows r - 3 for 3 <= r <= 513 (zeros otherwise) and emits decimated row i
+//     at r = 8 i + 9.
+//   * the step loop has two bodies, both branch free: the PLAIN one for iterations in which every lane is on a row
+//     4 <= r <= 509 (90 % of a frame; no row tests at all) and the general one, in which the row number selects
+//     restarts, divisor-3 inputs and zero feeds per lane (see iteration_is_plain and lane_step).
+//   * deferred power-of-two scaling: planes stay unscaled (x4 per pass), divisor-3 outputs become 4 * div3(s) = edge3(s),
+//     the single multiply by 2^-8 happens on the 4096 emitted values.
 //
 // Raw staging.  Stream row s of lane group G' = l >> 2 (4 lanes, 192 + 16 bytes of the row) lives in slot s & 15
 // of that group's ring; TMA boxes of 4 stream rows x kSegPitch bytes, one per group per EVENT E covering the
@@ -173,10 +177,10 @@ constexpr int kGroups = 32 / kGroupLanes;  // 8
 #ifndef VPDQS_BODY
 #define VPDQS_BODY 8
 #endif
-constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 4, 5, 6 or 8 (see LaneState)
-constexpr int kHistSlots = kBody;    // slots of the 4-deep column-pass histories (> 4: the slot written differs from the one read)
-constexpr int kFirstStep = -((8 + kBody - 1) / kBody) * kBody;  // the step loop starts here (a multiple of kBody <= -8;
-                                                                // steps < 0 only prepare lane 0's first row)
+constexpr int kBody = VPDQS_BODY;    // steps per iteration of the step loop: 8 (4 is kept for A/B runs; see LaneState)
+static_assert(kBody == 4 || kBody == 8, "the TMA events are placed every 4 steps, statically");
+constexpr int kHistSlots = kBody;    // slots of the 4-deep column-pass histories (8: the slot written differs from the one read)
+constexpr int kFirstStep = -8;       // the step loop starts here (a multiple of kBody; steps < 0 only prepare lane 0's first row)
 constexpr int kIssueLead = kRing - 6; // ISSUE(E) at step 4 E - 10 (ring of 16 rows; 4 E - 6 with 12): the earliest step at
                                      // which no lane still reads the box slot being refilled
 constexpr int kWaitLead = 2;         // WAIT(E)  at step 4 E - 2 (a step reads the raw rows of the NEXT step: its lumas are
@@ -258,7 +262,7 @@ constexpr int kPlainLastA = kImageRows - 3 - (kBody - 1);  // lane 0 stays on ro
 constexpr int kPlainLastB = kImageRows - kBoxRows - plain_event_row(kBody - 4);  // the LAST event's group-0 rows are <= 511
 constexpr int kPlainLast = kPlainLastA < kPlainLastB ? kPlainLastA : kPlainLastB;  // 496 (body of 4 steps, ring of 16 rows)
 VPDQS_HD bool iteration_is_plain(int f0, int r0, int n_frames) {
-    return kBody % 4 == 0 && (unsigned)f0 < (unsigned)n_frames && r0 >= kPlainFirst && r0 <= kPlainLast;
+    return (unsigned)f0 < (unsigned)n_frames && r0 >= kPlainFirst && r0 <= kPlainLast;
 }
 // consecutive plain iterations from r0 on (the kernel runs them as one inner loop)
 VPDQS_HD int plain_run_length(int r0) { return (kPlainLast - r0) / kBody + 1; }
@@ -277,17 +281,16 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
 // The step loop is unrolled by kBody and a step is compiled per position T in the body, so that every index below is
 // static.  The 4-deep histories of the column passes live in kHistSlots = kBody slots: the value fed at step u sits in
 // slot u mod kHistSlots, a step reads slot (u - 4) and writes slot u.  With 4 slots those are the same registers -- the
-// new value is produced while the old one is still needed, and ptxas has to park it and copy (16 MOVs per step);
-// with 5 or 8 slots it is computed straight into its final register.  Measured on B200: 8 slots (8-step body) save
-// the copies but the hot path (35 KB) overflows the 32 KB L1.5 instruction cache ("no_instructions" stalls 3 % ->
-// 19 %, 2 % slower overall); 5 slots (5-step body) keep the body small.
+// new value is produced while the old one is still needed, and ptxas has to park it and copy (20 MOVs per step);
+// with 8 slots it is computed straight into its final register.  The 8-step plain loop is 29 KB of code, just inside
+// the 32 KB instruction cache (an earlier 35 KB version of it was not: "no_instructions" stalls 3 % -> 19 %).
 struct LaneState {
     F2 s2[kCols / 2];         // P2 running sums: columns (2p, 2p+1) of the lane packed in one register pair.  At the start
                               // of a step they are ALSO the P2 outputs of the previous step, which P3 consumes in this one
                               // (one value for both: see the tail of lane_step for the divisor-3 rows)
     F2 h2[kHistSlots][kCols / 2];  // P2 histories (the last four inputs): the value fed at step u is h2[u mod kHistSlots]
-    F2 x[kBody % 2 == 0 ? 2 : 1][kCols / 2];  // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous
-                              // step; alternating sets x[step & 1] when the body is even
+    F2 x[2][kCols / 2];       // lumas of THIS step's row (pixels 16 l + 2 ..), computed during the previous step:
+                              // alternating sets x[step & 1]
     F2 keep;                  // the decimated pair a lane produces during an iteration of 8 steps (exactly one in a plain
     bool have;                // iteration: its rows advance by 8; at most one otherwise), stored once after the last step
     F2 s4;                    // P4 running sums of the two decimated columns 2l, 2l+1
@@ -306,7 +309,7 @@ struct LaneState {
             s2[p] = f2_splat(0.0f);
             VPDQS_UNROLL
             for (int j = 0; j < kHistSlots; ++j) h2[j][p] = f2_splat(0.0f);
-            x[0][p] = x[kBody % 2 == 0 ? 1 : 0][p] = f2_splat(0.0f);
+            x[0][p] = x[1][p] = f2_splat(0.0f);
         }
         s4 = keep = f2_splat(0.0f);
         VPDQS_UNROLL
@@ -378,7 +381,7 @@ template <int CH, int T, bool PLAIN, typename Emit>
 VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int lane, int n_frames, RowChain& out1,
                         RowChain& out3, Emit emit) {
     constexpr int JW = hist_slot(T), JR = hist_slot(T - 4);            // history slot written / read by this step
-    constexpr int XR = kBody % 2 == 0 ? (T & 1) : 0, XW = kBody % 2 == 0 ? XR ^ 1 : 0;  // luma set read / written
+    constexpr int XR = T & 1, XW = XR ^ 1;                             // luma set read / written
     const int r = PLAIN ? L.r + T : L.r;
     const bool live = PLAIN || (unsigned)L.f < (unsigned)n_frames;
     const bool edge_row = !PLAIN && (r == 3 || r == kImageRows + 1);

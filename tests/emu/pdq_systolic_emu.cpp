@@ -212,7 +212,7 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 }
             }
         }
-        if (kBody % 4 == 0 && F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
+        if (F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
         for (int E = waited + 1; E <= issued; ++E) W->wait(E);
         if (!W->pending.empty()) ++errors;
         for (int l = 0; l < 32; ++l)
