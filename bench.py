@@ -401,8 +401,9 @@ def run_b200(args) -> None:
                     "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
                     "traffic_source": "profiles/r02_traffic.json (ncu --set full dram__bytes_read+write, per frame x "
                                       "frames per launch)",
-                    "note": "one warp per frame, row-pass chain state handed lane to lane: no shared-memory transposes; "
-                            "bound by instruction issue (serial fp32 running sums), see DESIGN.md 4.2"}
+                    "note": "one warp per frame, row-pass chain state handed lane to lane: no shared-memory transposes; two "
+                            "branch-free loop bodies (plain rows / frame boundaries); bound by instruction issue (half-rate "
+                            "packed fp32 and byte-unpack operations of the exact running sums), see DESIGN.md 4.1"}
 
         # ---- end to end through the host-pointer C ABI (pinned host memory) ----
         import ctypes as C
