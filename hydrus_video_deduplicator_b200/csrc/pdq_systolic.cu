@@ -182,16 +182,22 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     // stream position of lane 0 at the first step of the iteration (uniform)
     int f0 = -1, r0 = kStepsPerFrame + kFirstStep;
     int plain_y = 0;  // see the plain run below
+    bool landed = false;
 
     // One step.  PLAIN (pdq_systolic_core.h, iteration_is_plain): every window is staged, the event is one 3-D box.
     auto step = [&](int t, auto jtag, auto ptag) {
         constexpr int T = decltype(jtag)::value;
         constexpr bool PLAIN = decltype(ptag)::value;
         // events every 4 steps, at a compile-time position in the body
+        // one step before an event: probe its barrier, so that the (normal) answer "landed" costs no latency there
+        if ((T & 3) == kEventPhase - 1) {
+            const int Ew = (t + 1 + kWaitLead) >> 2;
+            landed = (PLAIN || Ew >= 0) ? mbar_try_wait(bar0 + 8 * (Ew & 1), (uint32_t)((Ew >> 1) & 1)) : true;
+        }
         if ((T & 3) == kEventPhase) {
             const int Ew = (t + kWaitLead) >> 2, Ei = (t + kIssueLead) >> 2;
             if (PLAIN || Ew >= 0) {
-                wait(Ew);
+                if (!landed) wait(Ew);
                 waited = Ew;
             }
             if (PLAIN) {
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(kSysThreads, 1)
                     mbar_expect_tx(bar, kGroups * R::kBoxBytes);
                     tma_load_3d(ring + box_slot_of(Ei) * (kGroups * R::kBoxBytes), &tmap3, 0, plain_y + t, 0, bar);
                 }
-                __syncwarp();
+                __syncwarp();  // (measured: leaving it out is 1 % slower)
             } else {
                 issue(Ei);
             }
