@@ -17,6 +17,8 @@ using namespace vpdq_sys;
 
 namespace {
 
+bool g_general_only = false;  // model VPDQ_B200_SYSTOLIC_3D=0: no plain iterations, every event as per-group boxes
+
 template <int CH>
 struct WarpSim {
     using R = Raw<CH>;
@@ -41,7 +43,7 @@ struct WarpSim {
     void issue(int E) {
         const int s00 = box_first_row(E, 0);
         const int f0 = s00 / kStepsPerFrame, r00 = s00 % kStepsPerFrame;
-        if (s00 >= 0 && event_is_one_box(f0, r00, F)) {
+        if (!g_general_only && s00 >= 0 && event_is_one_box(f0, r00, F)) {
             // ONE 3-D box (x, row, g') at (0, Y0 - 28, 0): element address = kBase3 + x + kRowBytes*y + kStride3*g'
             ++one_box_events;
             Pending p{E, box_ring_offset<CH>(kGroups - 1, E), kGroups * R::kBoxBytes, std::vector<uint8_t>(kGroups * R::kBoxBytes), {}, {}};
@@ -169,7 +171,7 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
         for (int t = kFirstStep; t <= t_last || (t - kFirstStep) % kBody != 0; ++t) {  // (the kernel finishes its last body)
             const int T = (t - kFirstStep) % kBody;  // position in the loop body (kFirstStep is a multiple of kBody)
             if (T == 0) {
-                plain = iteration_is_plain(f0, r0, F);
+                plain = !g_general_only && iteration_is_plain(f0, r0, F);
                 plain_iterations += plain;
                 ++iterations;
             }
@@ -212,12 +214,12 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
                 }
             }
         }
-        if (F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
+        if (!g_general_only && F > 1 && plain_iterations * 10 < iterations * 8) ++errors;  // the plain body must be the common one
         for (int E = waited + 1; E <= issued; ++E) W->wait(E);
         if (!W->pending.empty()) ++errors;
         for (int l = 0; l < 32; ++l)
             if (optr[l] != a64 + (size_t)(f_begin + F) * 4096 + 2 * l) ++errors;  // every decimated row was emitted, in order
-        if (F > 1 && W->one_box_events < 100 * F) ++errors;  // the one-box path must be the common one
+        if (!g_general_only && F > 1 && W->one_box_events < 100 * F) ++errors;  // the one-box path must be the common one
         errors += W->errors;
         delete W;
     }
@@ -227,6 +229,8 @@ int emu_run(const uint8_t* frames, long long n_frames, int n_warps, float* a64) 
 
 // channels = 3: frames [n][512][512][3] RGB24; channels = 1: [n][512][512] 8-bit gray.  n_warps = warps the batch is
 // split over (the kernel: grid x 8).
+extern "C" __attribute__((visibility("default"))) void emu_systolic_general_only(int on) { g_general_only = on != 0; }
+
 extern "C" __attribute__((visibility("default"))) int emu_systolic_a64(const uint8_t* frames, long long n_frames,
                                                                        int n_warps, float* a64, int channels) {
     return channels == 3 ? emu_run<3>(frames, n_frames, n_warps, a64) : emu_run<1>(frames, n_frames, n_warps, a64);

@@ -75,20 +75,27 @@ def emu_sys():
                     str(EMU_DIR / "pdq_systolic_emu.cpp")], check=True)
     lib = C.CDLL(str(so))
     lib.emu_systolic_a64.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int]
+    lib.emu_systolic_general_only.argtypes = [C.c_int]
     return lib
 
 
-@pytest.mark.parametrize("n_frames,n_warps,channels", [(1, 1, 3), (2, 1, 3), (4, 1, 3), (3, 2, 3), (5, 8, 3),
-                                                       (1, 1, 1), (3, 2, 1), (4, 1, 1)])
-def test_emulated_systolic_schedule_is_bit_exact(emu_sys, n_frames, n_warps, channels):
+@pytest.mark.parametrize("n_frames,n_warps,channels,general_only", [
+    (1, 1, 3, False), (2, 1, 3, False), (4, 1, 3, False), (3, 2, 3, False), (5, 8, 3, False), (1, 1, 1, False),
+    (3, 2, 1, False), (4, 1, 1, False), (3, 1, 3, True), (2, 3, 1, True)])
+def test_emulated_systolic_schedule_is_bit_exact(emu_sys, n_frames, n_warps, channels, general_only):
     """kx_systolic_jarosz (one warp per frame, chain state handed lane to lane, per-group TMA rings): several
     frames streamed back to back through one warp (the zero rows between frames must flush every column chain),
     warps without frames, RGB24 and gray.  The emulator counts a read of a ring slot that is in flight or holds
-    another stream row as an error."""
+    another stream row as an error, and checks per lane what a plain iteration takes for granted.  general_only: no
+    iteration is plain and every TMA event is per-group boxes (the kernel under VPDQ_B200_SYSTOLIC_3D=0)."""
     frames = synth.synth_frames(n_frames, seed=57 + n_frames, channels=channels)
     a64 = np.full((n_frames, 64, 64), np.nan, np.float32)
-    errors = emu_sys.emu_systolic_a64(frames.ctypes.data_as(C.c_void_p), n_frames, n_warps,
-                                      a64.ctypes.data_as(C.c_void_p), channels)
+    emu_sys.emu_systolic_general_only(int(general_only))
+    try:
+        errors = emu_sys.emu_systolic_a64(frames.ctypes.data_as(C.c_void_p), n_frames, n_warps,
+                                          a64.ctypes.data_as(C.c_void_p), channels)
+    finally:
+        emu_sys.emu_systolic_general_only(0)
     assert errors == 0
     assert not np.isnan(a64).any(), "some decimated outputs were never written"
     for f in range(n_frames):

@@ -369,6 +369,37 @@ def test_kernel_is_deterministic_under_load(torch_dev):
     assert _ffi.debug_flags(0) == 0  # no TMA wait ever timed out
 
 
+def test_general_loop_body_alone_matches_oracle():
+    """The systolic kernel has two loop bodies: the plain one (88 % of the iterations) and the general, row-selecting
+    one.  With VPDQ_B200_SYSTOLIC_3D=0 (read once per process: hence a child) no iteration is plain and every TMA event
+    is eight 2-D boxes: the general body and the split events must produce every bit on their own -- RGB24 and gray,
+    frame counts that give warps 1, 2 and 3 frames."""
+    import subprocess
+    import sys
+
+    child = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "import oracle\n"
+        "from tests import synth\n"
+        "from hydrus_video_deduplicator_b200 import device\n"
+        "bad = 0\n"
+        "for n, ch in ((5, 3), (300, 3), (2400, 3), (7, 1), (1300, 1)):\n"
+        "    frames = synth.synth_frames(min(n, 24), seed=77 + n, channels=ch)\n"
+        "    reps = -(-n // frames.shape[0])\n"
+        "    batch = np.concatenate([frames] * reps)[:n]\n"
+        "    h, q = device.hash_frames(torch.from_numpy(batch).cuda())\n"
+        "    rgb = frames if ch == 3 else np.repeat(frames[..., None], 3, axis=3)\n"
+        "    ref_h, ref_q = oracle.pdq_hash_frames(rgb, nthreads=4)\n"
+        "    want_h = np.concatenate([ref_h] * reps)[:n]; want_q = np.concatenate([ref_q] * reps)[:n]\n"
+        "    bad += int(h.cpu().numpy().tobytes() != want_h.tobytes()) + int((q.cpu().numpy() != want_q).any())\n"
+        "print('MISMATCHES', bad)\n"
+    ) % str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    env = dict(__import__("os").environ, VPDQ_B200_SYSTOLIC_3D="0")
+    out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600, env=env)
+    assert "MISMATCHES 0" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("n_frames,channels", [(1, 3), (2, 3), (3, 3), (7, 3), (147, 3), (149, 3), (297, 3), (1000, 3),
                                                (1185, 3), (2500, 3), (1, 1), (150, 1), (601, 1)])
 def test_legacy_pipelines_agree(torch_dev, n_frames, channels):
