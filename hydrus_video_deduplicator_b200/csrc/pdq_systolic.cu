@@ -6,10 +6,15 @@
 //     row by row.  Lane l owns image columns 16 l .. 16 l + 15: the column passes are private running sums in
 //     registers, the row passes run along the lanes -- the chain state (5 floats per pass) moves to the next
 //     lane with one rotate-shuffle per step, so lane l works on stream row t - l at step t;
-//   * raw rows are staged by TMA (cp.async.bulk.tensor.2d; SASS UTMALDG.2D): per warp 8 lane-group rings of 16
-//     stream rows x 224 bytes, filled by boxes of 4 rows, one mbarrier per event (8 boxes), 8 steps of lead, two
-//     events in flight.  A lane reads its 54-byte window of its row with 4 LDS.128;
-//   * results (the decimated plane a64 [n][64][64] f32) go straight from registers to global memory.
+//   * raw rows are staged by TMA (cp.async.bulk.tensor.3d / .2d; SASS UTMALDG.3D / .2D): per warp 8 lane-group rings
+//     of 16 stream rows x 224 bytes, filled by boxes of 4 rows -- in the common case all eight group boxes of an event
+//     are ONE 3-D box -- one mbarrier per event, 8 steps of lead, two events in flight.  A lane reads its 54-byte
+//     window of its row with 4 LDS.128;
+//   * the step loop has two bodies of 8 steps, both branch free: runs of PLAIN iterations (every lane on a row
+//     4..509 of a live frame, one-box events: 88 % of a frame) are an inner loop of their own without a single row
+//     test; the general body handles the rare rows per lane by what the row number selects (pdq_systolic_core.h);
+//   * results (the decimated plane a64 [n][64][64] f32) go straight from registers to global memory, one store per
+//     lane and iteration.
 //
 // Same arithmetic, same order, bit-identical results as the oracle (and as the tiled kernels it replaces).
 #include <cuda.h>
@@ -188,8 +193,8 @@ __global__ void __launch_bounds__(kSysThreads, 1)
     auto step = [&](int t, auto jtag, auto ptag) {
         constexpr int T = decltype(jtag)::value;
         constexpr bool PLAIN = decltype(ptag)::value;
-        // events every 4 steps, at a compile-time position in the body
-        // one step before an event: probe its barrier, so that the (normal) answer "landed" costs no latency there
+        // events every 4 steps, at a compile-time position in the body.  One step before an event: probe its barrier,
+        // so that the (normal) answer "landed" costs no latency there
         if ((T & 3) == kEventPhase - 1) {
             const int Ew = (t + 1 + kWaitLead) >> 2;
             landed = (PLAIN || Ew >= 0) ? mbar_try_wait(bar0 + 8 * (Ew & 1), (uint32_t)((Ew >> 1) & 1)) : true;
