@@ -150,6 +150,13 @@ VPDQS_HD float edge3(float v) {
     return ffma(r, c4, q);
 }
 constexpr float kEdge3C = 1.33333337306976318f;
+// edge3 with its two constants as arguments: (kEdge3C, -0.75) -> edge3(v); (1, -1) -> v itself, exactly (q = v * 1,
+// the residual v - 1 * q = +0, q + 0 * c = v)
+VPDQS_HD float edge3_if(float v, float c, float k) {
+    const float q = fmul(v, c);
+    const float r = ffma(k, q, v);
+    return ffma(r, kEdge3C, q);
+}
 // the same on a packed pair, with the constants as arguments: (kEdge3C, -0.75) -> edge3(v); (1, -1) -> v itself, exactly
 // (no multiply feeds an add here: nothing for ptxas to contract)
 VPDQS_HD F2 edge3_if(F2 v, float c, float k) {
@@ -277,6 +284,32 @@ VPDQS_HD float row_feed(RowChain& c, float v) {
     c.h0 = c.h1; c.h1 = c.h2; c.h2 = c.h3; c.h3 = v;
     return c.s;
 }
+// The same with parts of the state switched off by multipliers that are 1 or 0 -- exact: x * 1 + y rounds once like
+// x + y, and x * 0 + y = y for finite x (every value here is finite and >= +0) -- instead of a select per value:
+//   row_feed_kh: the oldest history value counts kh times.  The first feeds of a lane subtract what the previous lane
+//                handed over; lane 0 must see zeros there, not what lane 31 rotates into it (nkh = -kh);
+//   row_feed_ks: also the incoming running sum counts ks times (P3: lane 0 starts a fresh chain);
+//   row_feed_kv: the new value counts kv times in the sum (lane 31's last two inputs are the drain zeros of its row;
+//                the registers hold the NEXT row's pixels 0, 1, which go into the history unmasked: exactly the state
+//                lane 0 needs next).
+VPDQS_HD float row_feed_kh(RowChain& c, float v, float nkh) {
+    c.s = fadd(c.s, v);
+    c.s = ffma(c.h0, nkh, c.s);
+    c.h0 = c.h1; c.h1 = c.h2; c.h2 = c.h3; c.h3 = v;
+    return c.s;
+}
+VPDQS_HD float row_feed_ks(RowChain& c, float v, float ks, float nkh) {
+    c.s = ffma(c.s, ks, v);
+    c.s = ffma(c.h0, nkh, c.s);
+    c.h0 = c.h1; c.h1 = c.h2; c.h2 = c.h3; c.h3 = v;
+    return c.s;
+}
+VPDQS_HD float row_feed_kv(RowChain& c, float v, float kv) {
+    c.s = ffma(v, kv, c.s);
+    c.s = fsub(c.s, c.h0);
+    c.h0 = c.h1; c.h1 = c.h2; c.h2 = c.h3; c.h3 = v;
+    return c.s;
+}
 
 // The step loop is unrolled by kBody and a step is compiled per position T in the body, so that every index below is
 // static.  The 4-deep histories of the column passes live in kHistSlots = kBody slots: the value fed at step u sits in
@@ -391,20 +424,24 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
     const float edge_c = edge_row ? kEdge3C : 1.0f, edge_k = edge_row ? -0.75f : -1.0f;
     RowChain c1 = L.in1, c3 = L.in3;
     float z0 = 0.0f, z1 = 0.0f;
-    const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u, first = lane == 0 ? 0xFFFFFFFFu : 0u;
+    const uint32_t last = lane == 31 ? 0xFFFFFFFFu : 0u;
+    // per-lane constants (hoisted out of the step loop): lane 0 ignores the chain history rotated into it, lane 31
+    // feeds the drain zeros; columns 0 (lane 0) and 510 (lane 31) of P1 have divisor 3
+    const float kf = lane == 0 ? 0.0f : 1.0f, nkf = -kf, k31 = lane == 31 ? 0.0f : 1.0f;
+    const float e0c = lane == 0 ? kEdge3C : 1.0f, e0k = lane == 0 ? -0.75f : -1.0f;
+    const float e31c = lane == 31 ? kEdge3C : 1.0f, e31k = lane == 31 ? -0.75f : -1.0f;
     // lane 31: its last two lumas are the NEXT row's pixels 0, 1 (its own row has only the drain zeros left there)
     const float xa = L.x[XR][7].x, xb = L.x[XR][7].y;
     VPDQS_UNROLL
     for (int p = 0; p < kCols / 2; ++p) {
         const int k = 2 * p;
-        F2 x = L.x[XR][p];
+        const F2 x = L.x[XR][p];
         L.x[XW][p] = luma_pair_at<CH>(w, Raw<CH>::kSkip + CH * k);  // next step's pixels 16 l + 2 + k, + 1
-        if (p == 7) x = F2{bitkeep(~last, x.x), bitkeep(~last, x.y)};
         // P1: row pass 1 along the lanes -> output columns 16 l + k, + 1 (unscaled, x4)
-        float v0 = row_feed(c1, x.x);
-        if (p == 0) v0 = bitsel(first, edge3(v0), v0);  // column 0: divisor 3
-        if (p == 7) v0 = bitsel(last, edge3(v0), v0);   // column 510: divisor 3 (column 511 feeds no decimated output)
-        const float v1 = row_feed(c1, x.y);
+        float v0 = p == 0 ? row_feed_kh(c1, x.x, nkf) : (p == 7 ? row_feed_kv(c1, x.x, k31) : row_feed(c1, x.x));
+        if (p == 0) v0 = edge3_if(v0, e0c, e0k);    // column 0: divisor 3
+        if (p == 7) v0 = edge3_if(v0, e31c, e31k);  // column 510: divisor 3 (column 511 feeds no decimated output)
+        const float v1 = p == 0 ? row_feed_kh(c1, x.y, nkf) : (p == 7 ? row_feed_kv(c1, x.y, k31) : row_feed(c1, x.y));
         // P2: column pass 1, private -> output row r - 2 (unscaled, x16)
         const F2 v{v0, v1};
         const F2 old = L.h2[JR][p], prev = L.s2[p];
@@ -417,10 +454,13 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
         // (rare rows: edge3 with its two constants switched to 1 on every other row, which makes it the identity --
         // q = prev * 1, the residual prev - 1 * q = +0, q + 0 * c = prev -- without a select per value)
         const F2 pin = PLAIN ? prev : edge3_if(prev, edge_c, edge_k);
-        const float u0 = row_feed(c3, pin.x);
+        const float u0 = p == 0 ? row_feed_ks(c3, pin.x, kf, nkf) : (p == 1 ? row_feed_kh(c3, pin.x, nkf) : row_feed(c3, pin.x));
         if (k == 6) z0 = u0;
         if (k == 14) z1 = u0;
-        row_feed(c3, pin.y);
+        if (p <= 1)
+            row_feed_kh(c3, pin.y, nkf);
+        else
+            row_feed(c3, pin.y);
     }
     // P4: column pass 2, private, fed P3 row r - 3 (zeros unless real) -> output row r - 5
     {
@@ -441,11 +481,11 @@ VPDQS_HD void lane_step(LaneState& L, const uint32_t (&w)[Raw<CH>::kWords], int 
             emit(fmul(s.x, 0.00390625f), fmul(s.y, 0.00390625f));
         }
     }
-    // hand-over (lane 31 -> lane 0, next row: the chain after the prologue pixels 0, 1, fed without output / a fresh chain)
-    out1 = RowChain{bitsel(last, fadd(xa, xb), c1.s), bitkeep(~last, c1.h0), bitkeep(~last, c1.h1), bitsel(last, xa, c1.h2),
-                    bitsel(last, xb, c1.h3)};
-    out3 = RowChain{bitkeep(~last, c3.s), bitkeep(~last, c3.h0), bitkeep(~last, c3.h1), bitkeep(~last, c3.h2),
-                    bitkeep(~last, c3.h3)};
+    // hand-over.  Lane 31 -> lane 0 is the next row: its P1 chain starts after the prologue pixels 0, 1 (fed without
+    // output): sum xa + xb, history (0, 0, xa, xb) -- lane 31's own history already ends in (xa, xb), and lane 0 takes
+    // the two older values as zeros (row_feed_kh); its P3 chain starts fresh (row_feed_ks / row_feed_kh).
+    out1 = RowChain{bitsel(last, fadd(xa, xb), c1.s), c1.h0, c1.h1, c1.h2, c1.h3};
+    out3 = c3;
     if (PLAIN) {
         if (T == kBody - 1) L.r += kBody;
     } else {
